@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: BSB-100D FBSNN training iterations/s (FC-Sine 4x256, N=50)
+and Monte-Carlo basket paths/s, on N GPUs of one box.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm (CPU oracle port) on host cores
+
+One "step" = one training iteration (Brownian minibatch already resident in HBM for `value`; copied from pinned
+host memory inside the timed region for `e2e`).  Paths are sharded over ranks (strong scaling: the global batch
+M is fixed); the only collective is one sum-allreduce of [gradient | loss] per iteration.  Rank 0 prints ONE JSON
+line.  See DESIGN.md section "Measurement" for the algorithmic FLOP count (2.671 MFLOP per (path, step) row).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+D, NSTEPS, H, NLAYERS = 100, 50, 256, 4
+LAYERS = [D + 1] + NLAYERS * [H] + [1]
+FLOP_PER_ROW = 2.0 * 3 * ((D + 1) * H + 3 * H * H + H + D * H + 3 * H * H + H)   # 3(F + A) MACs, SURVEY section 8d
+METRIC = "BSB-100D FBSDE train iters/s"
+
+
+def xi_bsb():
+    return np.array([1.0, 0.5] * (D // 2))[None, :]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_train_rate(paths_global, sample_paths, steps, warmup):
+    """iters/s of the reference algorithm for a global batch of `paths_global`, measured on a bounded sample of
+    `sample_paths` paths per step (cost is linear in the number of paths: every path is an independent row
+    block) and scaled.  Runs the oracle's faithful op sequence (autograd double-backward, diag_embed sigma)."""
+    from oracle import fbsnn_oracle as orc
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+    sol = orc.OracleSolver("bsb", xi_bsb(), 1.0, sample_paths, NSTEPS, D, LAYERS, "FC", "Sine")
+    sol.make_optimizer(1e-3)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        t, W = sol.fetch_minibatch()
+        sol.train_step(t, W)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return (sample_paths / sec) / paths_global, sec
+
+
+def cpu_mc_rate(n_sample):
+    from oracle import mc_oracle as mco
+    np.random.seed(0)
+    corr = mco.random_correlation(D)
+    t0 = time.perf_counter()
+    mco.mc_price(np.ones(D), 0.05, 0.2, corr, True, np.ones(D) / D, 1.0, 1.0, NSTEPS, n_sample)
+    return n_sample / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    sample = args.cpu_sample_paths
+    value, sec = cpu_train_rate(args.paths, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {args.paths} paths per step ({sec:.2f} s/step measured), scaled "
+                                   f"linearly in paths; oracle port of DeepBSDE.py train loop, anomaly detection off"},
+        "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"BSB-100D FBSNN FC-Sine 4x256, M={args.paths} paths (global), N={NSTEPS} steps, Adam",
+            "paths": args.paths, "time_steps": NSTEPS, "dim": D, "precision": args.precision,
+            "l2_policy": "inputs larger than L2: each step reads a different resident minibatch "
+                         "(1.3 GB at M=65536) and streams GBs of sweep arrays"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import dnnpde_b200 as pde
+    from dnnpde_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = pde._lib.load()
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            tt = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt)
+        return x
+
+    M = args.paths
+    torch.manual_seed(1234)
+    sol = pde.BlackScholesBarenblatt(xi_bsb(), 1.0, M, NSTEPS, D, LAYERS, "FC", "Sine", precision=args.precision,
+                                     data_parallel=True)
+    lo, hi = parallel.shard_range(M, rank, world)
+    m_loc = hi - lo
+
+    # resident synthetic minibatches (reference layout, cumulative t and W), generated on the device
+    import ctypes
+    sp = sol._spec()
+    ws = sol._workspace(lib, sp, m_loc, True)
+    nbatch = 2
+    batches = []
+    for b in range(nbatch):
+        t = torch.empty(m_loc, NSTEPS + 1, 1, device=dev)
+        W = torch.empty(m_loc, NSTEPS + 1, D, device=dev)
+        rc = lib.fbsnn_fetch_minibatch(ctypes.byref(sp), 1.0, m_loc, lo, 777, b, None, ctypes.c_void_p(ws.data_ptr()),
+                                       ws.numel(), ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(W.data_ptr()),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        pde._lib.check(rc, "fbsnn_fetch_minibatch")
+        batches.append((t, W))
+    loss_buf = torch.zeros(args.warmup + args.steps + 8, device=dev)
+
+    # ---- value: K steps, inputs resident in HBM, CUDA events, max over ranks --------------------------------
+    sol.begin_training(1e-3)
+    for i in range(args.warmup):
+        t, W = batches[i % nbatch]
+        sol.training_step(t, W, loss_buf[i:i + 1])
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = lib.fbsnn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        t, W = batches[i % nbatch]
+        sol.training_step(t, W, loss_buf[args.warmup + i:args.warmup + i + 1])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = (lib.fbsnn_launch_count() - l0) // args.steps
+    clk = clocks.stop()
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+    final_loss = float(loss_buf[args.warmup + args.steps - 1])
+
+    # ---- roofline of the dominant kernel (dense-layer GEMM): per-launch CUDA events, live ---------------------
+    lib.fbsnn_dense_timing(1)
+    t, W = batches[0]
+    sol.training_step(t, W, loss_buf[-1:])
+    torch.cuda.synchronize()
+    out6 = (ctypes.c_double * 6)()
+    pde._lib.check(lib.fbsnn_dense_timing_read(out6), "timing")
+    lib.fbsnn_dense_timing(0)
+    n_dense, dense_ms, dense_flops = int(out6[0]), out6[1], out6[2]
+    achieved = dense_flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
+    tc_peak = pk["bf16"] * 0.5          # kind::tf32 issues at half the bf16 rate (nominal 1.1 vs 2.25 PFLOP/s)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": achieved / tc_peak, "traffic": None,
+                "kernel": "gemm_tc_kernel (tcgen05 kind::tf32)" if out6[3] > 0 else "gemm_simt_kernel (fp32 FMA)",
+                "launches_per_step": n_dense, "dense_ms_per_step": dense_ms,
+                "dense_share_of_step": dense_ms / ms_per_step,
+                "peak_source": f"{pk['source']} bf16 {pk['bf16']} TFLOP/s x 0.5 (tf32 rate)",
+                "step_tflops": FLOP_PER_ROW * m_loc * (NSTEPS + 1) / (ms_per_step * 1e-3) / 1e12}
+
+    # ---- e2e: the public train() API, minibatch copied from pinned host memory every step ---------------------
+    host = []
+    for b in range(nbatch):
+        host.append((batches[b][0].cpu().pin_memory(), batches[b][1].cpu().pin_memory()))
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    # fetch_minibatch() override: hands out the batch whose H2D copy was issued on the copy stream one call
+    # earlier and issues the next copy (double buffered); every byte crosses PCIe inside the timed region.
+    state = {"i": 0, "pending": None}
+
+    def issue(i):
+        th, Wh = host[i % nbatch]
+        with torch.cuda.stream(copy_stream):
+            td = torch.empty(th.shape, device=dev)
+            Wd = torch.empty(Wh.shape, device=dev)
+            td.copy_(th, non_blocking=True)
+            Wd.copy_(Wh, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return td, Wd, ev
+
+    def fetch():
+        if state["pending"] is None:
+            state["pending"] = issue(state["i"])
+        td, Wd, ev = state["pending"]
+        torch.cuda.current_stream().wait_event(ev)
+        td.record_stream(torch.cuda.current_stream()), Wd.record_stream(torch.cuda.current_stream())
+        state["i"] += 1
+        state["pending"] = issue(state["i"])
+        return td, Wd
+
+    sol.fetch_minibatch = fetch
+    sol.M = M
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol.train(max(1, args.warmup), 1e-3)
+        barrier()
+        t0 = time.perf_counter()
+        sol.train(args.steps, 1e-3)
+        barrier()
+        e2e_sec = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = args.steps / e2e_sec
+    h2d = int((host[0][0].numel() + host[0][1].numel()) * 4)
+    e2e = {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+           "api": "BlackScholesBarenblatt.train(K, lr) with host-supplied Brownian minibatches (pinned, "
+                  "double-buffered H2D on a copy stream)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "config": workload_config(args), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "final_loss": final_loss,
+    }
+
+    # ---- secondary metric: Monte-Carlo basket paths/s (D=100, N=50, correlated) -------------------------------
+    if not args.skip_mc:
+        np.random.seed(0)
+        model = pde.BlackScholesModel(0.05, 0.2, D, True)
+        pr = pde.MonteCarloPricer(model, pde.BasketOption(np.ones(D) / D, 1.0), 1.0, NSTEPS, args.mc_paths, seed=7,
+                                  data_parallel=True)
+        n_lo, n_hi = parallel.shard_range(args.mc_paths, rank, world)
+        pr.price_async(np.ones(D), max(1, (n_hi - n_lo) // 16), n_lo, 7)      # warm-up
+        barrier()
+        m0 = lib.mc_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sums = pr.price_async(np.ones(D), n_hi - n_lo, n_lo, 7)
+        e1.record()
+        barrier()
+        mc_ms = max_over_ranks(e0.elapsed_time(e1))
+        parallel.allreduce_sums(sums)
+        s, q = (float(v) for v in sums.cpu())
+        mean = s / args.mc_paths
+        se = float(np.sqrt(max(q / args.mc_paths - mean * mean, 0.0) / args.mc_paths))
+        pps = args.mc_paths / (mc_ms * 1e-3)
+        line["mc"] = {"metric": "MC basket paths/s", "value": pps, "unit": "paths/s", "paths": args.mc_paths,
+                      "ms": mc_ms, "price": mean, "stderr": se, "normals_per_s": pps * NSTEPS * D,
+                      "gpu_launches": int(lib.mc_launch_count() - m0),
+                      "form": "N*D Philox/Box-Muller normals per path, Cholesky matvec hoisted (L sum_t z_t)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample ----------------------
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        v, sec = cpu_train_rate(M, args.cpu_sample_paths, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "iters/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_sample_paths} of {M} paths per step ({sec:.2f} s/step), "
+                                          "scaled linearly in paths"}
+        if not args.skip_mc:
+            line["mc"]["cpu_baseline"] = {"value": cpu_mc_rate(20000), "unit": "paths/s", "cores": 1, "kind": "port",
+                                          "sample": "20000 paths, D=100, N=50"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--paths", type=int, default=65536, help="global number of Brownian paths M")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--mc-paths", type=int, default=1 << 28)
+    ap.add_argument("--cpu-sample-paths", type=int, default=256)
+    ap.add_argument("--skip-mc", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,20 @@
+"""B200-native (sm_100a) FBSNN training step and basket Monte-Carlo pricer behind the reference's Python surface.
+
+The directory name is not a Python identifier; import it with
+    importlib.import_module("deep-neural-network-solutions-for-partial-differential-equations_b200")
+or through the `dnnpde_b200` alias module at the repository root.
+"""
+from . import _lib, parallel, spec
+from .fbsnn import FBSNN
+from .mc_pricer import (AnalyticalBlackScholes, BasketOption, BlackScholesModel, CorrelationMatrix,
+                        MonteCarloPricer)
+from .networks import Naisnet, Sine
+from .problems import (BasketCallOption, BlackScholesBarenblatt, BSPDETestCase, CallOption1D, CallOptionND,
+                       HamiltonJacobiBellman, u_exact)
+
+build = _lib.build
+
+__all__ = ["FBSNN", "Sine", "Naisnet", "BlackScholesBarenblatt", "BasketCallOption", "BSPDETestCase",
+           "CallOption1D", "CallOptionND", "HamiltonJacobiBellman", "u_exact", "CorrelationMatrix",
+           "BlackScholesModel", "BasketOption", "MonteCarloPricer", "AnalyticalBlackScholes", "build",
+           "parallel", "spec"]

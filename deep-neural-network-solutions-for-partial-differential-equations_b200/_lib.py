@@ -1,0 +1,122 @@
+"""Loader (and in-tree builder) of the sm_100a CUDA library behind the C-ABI in include/fbsnn_b200.h.
+
+There is no CPU or PyTorch fallback: if the shared library is missing and cannot be built, or no CUDA device is
+present when a compute entry point is called, the caller gets a RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libfbsnn_b200.so")
+SOURCES = ["fbsnn_api.cu", "mc_pricer.cu"]
+HEADERS = ["common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "kernels.cuh", "philox.cuh",
+           os.path.join("..", "..", "include", "fbsnn_b200.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p) and os.path.getmtime(p) > t:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libfbsnn_b200.so next to this file (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libfbsnn_b200.so (and there is no CPU fallback)")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES + ["-lcuda"]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+def _declare(lib):
+    from . import spec as S
+    c = ctypes
+    vp, f32p, i64, u64, sz = c.c_void_p, c.c_void_p, c.c_int64, c.c_uint64, c.c_size_t
+    lib.fbsnn_last_error.restype = c.c_char_p
+    lib.fbsnn_last_error.argtypes = []
+    lib.fbsnn_version.restype = c.c_int
+    lib.fbsnn_launch_count.restype = c.c_longlong
+    lib.fbsnn_launch_count.argtypes = []
+    lib.fbsnn_dense_timing.restype = None
+    lib.fbsnn_dense_timing.argtypes = [c.c_int]
+    lib.fbsnn_dense_timing_read.restype = c.c_int
+    lib.fbsnn_dense_timing_read.argtypes = [c.POINTER(c.c_double)]
+    lib.fbsnn_workspace_bytes.restype = c.c_int
+    lib.fbsnn_workspace_bytes.argtypes = [c.POINTER(S.FbsnnSpec), i64, c.c_int, c.POINTER(sz)]
+    lib.fbsnn_fetch_minibatch.restype = c.c_int
+    lib.fbsnn_fetch_minibatch.argtypes = [c.POINTER(S.FbsnnSpec), c.c_float, i64, i64, u64, u64, f32p, vp, sz,
+                                          f32p, f32p, vp]
+    lib.fbsnn_net_u.restype = c.c_int
+    lib.fbsnn_net_u.argtypes = [c.POINTER(S.FbsnnSpec), f32p, f32p, f32p, i64, vp, sz, f32p, f32p, vp]
+    lib.fbsnn_forward.restype = c.c_int
+    lib.fbsnn_forward.argtypes = [c.POINTER(S.FbsnnSpec), f32p, f32p, f32p, f32p, i64, i64, vp, sz, f32p, f32p,
+                                  f32p, f32p, vp]
+    lib.fbsnn_loss_grad.restype = c.c_int
+    lib.fbsnn_loss_grad.argtypes = [c.POINTER(S.FbsnnSpec), f32p, f32p, f32p, f32p, f32p, i64, i64, c.c_float,
+                                    i64, u64, u64, f32p, vp, sz, f32p, f32p, f32p, f32p, vp]
+    lib.fbsnn_adam_step.restype = c.c_int
+    lib.fbsnn_adam_step.argtypes = [c.POINTER(S.FbsnnAdam), f32p, f32p, f32p, f32p, i64, vp, vp]
+    lib.fbsnn_train_step.restype = c.c_int
+    lib.fbsnn_train_step.argtypes = [c.POINTER(S.FbsnnSpec), c.POINTER(S.FbsnnAdam), f32p, f32p, f32p, f32p, vp,
+                                     f32p, f32p, f32p, i64, i64, c.c_float, i64, u64, u64, f32p, vp, sz, f32p,
+                                     f32p, f32p, vp]
+    lib.mc_launch_count.restype = c.c_longlong
+    lib.mc_launch_count.argtypes = []
+    lib.mc_scratch_bytes.restype = sz
+    lib.mc_scratch_bytes.argtypes = []
+    lib.mc_basket_price.restype = c.c_int
+    lib.mc_basket_price.argtypes = [c.POINTER(S.McSpec), f32p, f32p, f32p, u64, u64, u64, vp, vp, vp]
+    lib.mc_generate_paths.restype = c.c_int
+    lib.mc_generate_paths.argtypes = [c.POINTER(S.McSpec), f32p, f32p, u64, u64, u64, f32p, vp]
+
+
+EXPORTS = ["fbsnn_last_error", "fbsnn_version", "fbsnn_launch_count", "fbsnn_dense_timing",
+           "fbsnn_dense_timing_read", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
+           "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_adam_step", "fbsnn_train_step", "mc_scratch_bytes", "mc_launch_count",
+           "mc_basket_price", "mc_generate_paths"]
+
+
+def load():
+    """dlopen the library (building it first if it is missing and nvcc is available)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                build()
+            lib = ctypes.CDLL(LIB_PATH)
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().fbsnn_last_error().decode() or f"code {rc}"
+        if rc == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what}: {msg}")

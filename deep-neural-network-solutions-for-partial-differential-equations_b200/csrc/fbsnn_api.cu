@@ -1,0 +1,631 @@
+// C-ABI of the FBSNN step (include/fbsnn_b200.h): workspace plan, sweep orchestration, launches.
+//
+// Row r = m*(N+1) + n is one (path, step) point.  X does not depend on the network parameters for any of the
+// reference's problems, so all M*(N+1) rows are evaluated as one batch with four sweeps
+//   F (forward)  A (input adjoint -> Z = Du)  T (tangent in direction dL/dZ)  B (backward)
+// followed by the weight-gradient contractions G.  tests/passes_model.py states the same algebra on the host.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace fbsnn {
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU_CHECK(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess) return fail(FBSNN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));    \
+  } while (0)
+static long long g_launches = 0;  // kernels launched by this library since load (bench.py's gpu_launches)
+#define LAUNCH_CHECK(name)                                                                        \
+  do {                                                                                            \
+    ++g_launches;                                                                                 \
+    cudaError_t e_ = cudaGetLastError();                                                          \
+    if (e_ != cudaSuccess) return fail(FBSNN_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+constexpr int kMaxL = FBSNN_MAX_HIDDEN;
+
+struct Plan {
+  int D, N, L, ldx, ldi, d_in;
+  int H[kMaxL + 2];
+  bool nais;
+  long long rows;
+  int loss_blocks, col_blocks, col_rows_per_block, wg_split, wg_chunk, gsq_blocks;
+  // offsets in floats
+  size_t xin, sdw, Y, zf, V, ev, ybar, inc, zraw, part_loss, part_wg, part_col, part_gsq;
+  size_t g[kMaxL + 2], a[kMaxL + 2], delta[kMaxL + 2], szz[kMaxL + 2], hd[kMaxL + 2], h[kMaxL + 2],
+      ht[kMaxL + 2], hb[kMaxL + 2];
+  size_t Bm[kMaxL + 2], Rm[kMaxL + 2], Bbar[kMaxL + 2], Sm[kMaxL + 2], nstate[kMaxL + 2];
+  size_t total;
+};
+
+static int round_up(long long v, int m) { return (int)((v + m - 1) / m * m); }
+
+static int validate(const FbsnnSpec* s) {
+  if (!s) return fail(FBSNN_E_BADARG, "spec is null");
+  if (s->D < 1 || s->N < 1) return fail(FBSNN_E_BADARG, "need D >= 1 and N >= 1 (got D=%d N=%d)", s->D, s->N);
+  if (s->n_hidden < 1 || s->n_hidden > kMaxL) return fail(FBSNN_E_UNSUPPORTED, "n_hidden=%d outside 1..%d", s->n_hidden, kMaxL);
+  for (int l = 0; l < s->n_hidden; ++l)
+    if (s->width[l] < 4 || s->width[l] % 4) return fail(FBSNN_E_UNSUPPORTED, "hidden width %d is not a positive multiple of 4", s->width[l]);
+  if (s->net_kind == FBSNN_NET_NAIS) {
+    if (s->n_hidden < 2 || s->n_hidden > 4) return fail(FBSNN_E_UNSUPPORTED, "NAIS-Net needs 1..3 stable blocks");
+    for (int l = 1; l < s->n_hidden; ++l)
+      if (s->width[l] != s->width[0]) return fail(FBSNN_E_UNSUPPORTED, "NAIS-Net needs equal hidden widths");
+  } else if (s->net_kind != FBSNN_NET_FC) {
+    return fail(FBSNN_E_UNSUPPORTED, "unknown net_kind %d", s->net_kind);
+  }
+  if (s->act_kind < 0 || s->act_kind > 2) return fail(FBSNN_E_UNSUPPORTED, "unknown act_kind %d", s->act_kind);
+  if (s->mu_kind < 0 || s->mu_kind > 1 || s->sigma_kind < 0 || s->sigma_kind > 1 || s->phi_kind < 0 ||
+      s->phi_kind > 2 || s->g_kind < 0 || s->g_kind > 3)
+    return fail(FBSNN_E_UNSUPPORTED, "problem callables outside the closed enumeration");
+  if (s->precision != FBSNN_PREC_FP32 && s->precision != FBSNN_PREC_TF32)
+    return fail(FBSNN_E_UNSUPPORTED, "unknown precision %d", s->precision);
+  return 0;
+}
+
+static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& p) {
+  memset(&p, 0, sizeof(p));
+  p.D = s->D, p.N = s->N, p.L = s->n_hidden;
+  p.d_in = s->D + 1;
+  p.ldx = round_up(p.d_in, 4);
+  p.ldi = round_up(s->D, 4);
+  p.nais = s->net_kind == FBSNN_NET_NAIS;
+  p.rows = rows;
+  p.H[0] = p.d_in;
+  for (int l = 1; l <= p.L; ++l) p.H[l] = s->width[l - 1];
+  p.loss_blocks = (int)((rows + 7) / 8);
+  p.col_blocks = (int)std::min<long long>(std::max<long long>((rows + 63) / 64, 1), 1024);
+  p.col_rows_per_block = (int)((rows + p.col_blocks - 1) / p.col_blocks);
+  p.col_blocks = (int)((rows + p.col_rows_per_block - 1) / p.col_rows_per_block);
+  int split = (int)std::min<long long>(std::max<long long>((rows + 511) / 512, 1), 256);
+  p.wg_chunk = round_up((rows + split - 1) / split, 16);
+  p.wg_split = (int)((rows + p.wg_chunk - 1) / p.wg_chunk);
+  p.gsq_blocks = 256;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    size_t o = off;
+    off += (n + 63) / 64 * 64;  // 256-byte granules
+    return o;
+  };
+  const size_t R = (size_t)rows;
+  p.xin = take(R * p.ldx);
+  p.sdw = take(R * p.D);
+  p.Y = take(R);
+  p.zf = take(R * p.ldx);
+  p.part_loss = take(2 * (size_t)p.loss_blocks);
+  p.ev = take(R);
+  for (int l = 1; l <= p.L; ++l) {
+    p.g[l] = take(R * p.H[l]);
+    p.a[l] = take(R * p.H[l]);
+    p.delta[l] = take(R * p.H[l]);
+    p.h[l] = (p.nais && l >= 2) ? take(R * p.H[l]) : p.g[l];
+    if (p.nais && l >= 2 && l <= p.L - 1) p.ht[l] = take(R * p.H[l]);
+  }
+  if (p.nais)
+    for (int l = 2; l <= p.L; ++l) {
+      const size_t hh = (size_t)p.H[l] * p.H[l];
+      p.Bm[l] = take(hh), p.Rm[l] = take(hh), p.nstate[l] = take(4);
+    }
+  if (with_grad) {
+    p.V = take(R * p.ldx);
+    p.ybar = take(R);
+    p.inc = take(R * p.ldi);
+    p.zraw = take(R * p.ldi);
+    size_t wg = 0;
+    for (int l = 1; l <= p.L; ++l) {
+      p.szz[l] = take(R * p.H[l]);
+      p.hd[l] = take(R * p.H[l]);
+      if (p.nais && l >= 2 && l <= p.L - 1) p.hb[l] = take(R * p.H[l]);
+      wg = std::max(wg, (size_t)p.H[l] * (size_t)round_up(p.H[l - 1], 4));
+      wg = std::max(wg, (size_t)p.H[l] * (size_t)p.ldx);
+    }
+    p.part_wg = take(wg * p.wg_split);
+    p.part_col = take((size_t)kMaxColJobs * p.col_blocks * 1024);
+    p.part_gsq = take(p.gsq_blocks);
+    if (p.nais)
+      for (int l = 2; l <= p.L; ++l) {
+        const size_t hh = (size_t)p.H[l] * p.H[l];
+        p.Bbar[l] = take(hh), p.Sm[l] = take(hh);
+      }
+  }
+  p.total = off;
+}
+
+static ProblemK problem_k(const FbsnnSpec* s, const Plan& p) {
+  ProblemK k;
+  k.D = s->D, k.N = s->N, k.ldx = p.ldx;
+  k.mu_kind = s->mu_kind, k.sigma_kind = s->sigma_kind, k.phi_kind = s->phi_kind, k.g_kind = s->g_kind;
+  k.mu_c = s->mu_c, k.sigma_c = s->sigma_c, k.phi_c = s->phi_c, k.strike = s->strike;
+  return k;
+}
+
+// Optional per-launch timing of the dense layers (bench.py's roofline leg): when enabled, every dense() call is
+// bracketed by CUDA events on its stream; fbsnn_dense_timing_read() sums them after a synchronise.
+constexpr int kMaxTimed = 4096;
+static bool g_timing = false;
+static int g_ntimed = 0;
+static cudaEvent_t g_ev0[kMaxTimed], g_ev1[kMaxTimed];
+static double g_flops[kMaxTimed];
+static bool g_timed_tc[kMaxTimed];
+
+// dense layer dispatch: SIMT fp32, or tcgen05 TF32 when the variant is selected and the shape qualifies
+template <bool A_KC, bool B_KC, class Epi>
+static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nsplit, cudaStream_t st, const char* what) {
+  const bool tc = s->precision == FBSNN_PREC_TF32 && tc_eligible<A_KC, B_KC>(g, nsplit);
+  int slot = -1;
+  if (g_timing && g_ntimed < kMaxTimed) {
+    slot = g_ntimed++;
+    if (!g_ev0[slot]) cudaEventCreate(&g_ev0[slot]), cudaEventCreate(&g_ev1[slot]);
+    double k = 0;
+    for (int i = 0; i < g.nseg; ++i) k += g.seg[i].K;
+    g_flops[slot] = 2.0 * (double)g.M * (double)g.N * k;   // algorithmic FLOPs of this launch (padding included in N)
+    g_timed_tc[slot] = tc;
+    cudaEventRecord(g_ev0[slot], st);
+  }
+  ++g_launches;
+  cudaError_t e = tc ? launch_gemm_tc<A_KC, B_KC>(g, epi, num_sms(), st) : launch_gemm<A_KC, B_KC>(g, epi, nsplit, num_sms(), st);
+  if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
+  if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "%s gemm %s: %s", tc ? "tcgen05" : "simt", what, cudaGetErrorString(e));
+  return 0;
+}
+
+struct Net {
+  const float* W[kMaxL + 2];    // main matrix of layer l as (H_l x H_{l-1}) row-major: FC W_l, NAIS l>=2: Bm_l
+  const float* Wraw[kMaxL + 2];
+  const float* Win[kMaxL + 2];
+  const float* b[kMaxL + 2];
+  const float* bin[kMaxL + 2];
+  const float* wout;
+  const float* bout;
+};
+
+static Net bind_net(const FbsnnSpec* s, const Plan& p, const float* params, float* ws) {
+  Net n;
+  memset(&n, 0, sizeof(n));
+  for (int l = 1; l <= p.L; ++l) {
+    n.Wraw[l] = params + s->off_W[l];
+    n.b[l] = params + s->off_b[l];
+    if (p.nais && l >= 2) {
+      n.W[l] = ws + p.Bm[l];
+      n.Win[l] = params + s->off_Win[l];
+      n.bin[l] = params + s->off_bin[l];
+    } else {
+      n.W[l] = n.Wraw[l];
+    }
+  }
+  n.wout = params + s->off_W[p.L + 1];
+  n.bout = params + s->off_b[p.L + 1];
+  return n;
+}
+
+// NAIS projection, once per call: Bm_l = -(s W_l^T W_l + eps I)
+static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, cudaStream_t st) {
+  for (int l = 2; l <= p.L; ++l) {
+    const int H = p.H[l];
+    GemmArgs g{};
+    g.nseg = 1, g.M = H, g.N = H, g.Nb = H, g.kchunk = 0;
+    g.seg[0] = GemmSeg{n.Wraw[l], n.Wraw[l], H, H, H};
+    int rc = dense<false, false>(s, g, EpiStore{ws + p.Rm[l], H}, 1, st, "nais RtR");
+    if (rc) return rc;
+    nais_project_kernel<<<1, 1024, 0, st>>>(ws + p.Rm[l], H, s->nais_eps, ws + p.Bm[l], ws + p.nstate[l]);
+    LAUNCH_CHECK("nais_project");
+  }
+  return 0;
+}
+
+// F and A sweeps over `rows` rows whose inputs are already in ws[xin]; leaves Y in ws[Y], Du_full in ws[zf].
+static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, bool with_grad, cudaStream_t st) {
+  const int R = (int)p.rows;
+  const int act = s->act_kind;
+  for (int l = 1; l <= p.L; ++l) {
+    GemmArgs g{};
+    g.M = R, g.N = p.H[l], g.Nb = p.H[l], g.kchunk = 0;
+    if (l == 1) {
+      g.nseg = 1;
+      g.seg[0] = GemmSeg{ws + p.xin, n.W[1], p.ldx, p.d_in, p.d_in};
+    } else {
+      g.nseg = 1;
+      g.seg[0] = GemmSeg{ws + p.h[l - 1], n.W[l], p.H[l - 1], p.H[l - 1], p.H[l - 1]};
+      if (p.nais) {
+        g.nseg = 2;
+        g.seg[1] = GemmSeg{ws + p.xin, n.Win[l], p.ldx, p.d_in, p.d_in};
+      }
+    }
+    EpiFwd e{};
+    e.bias1 = n.b[l], e.bias2 = n.bin[l];
+    const bool res = p.nais && l >= 2;
+    e.res = res ? ws + p.h[l - 1] : nullptr;
+    e.g = ws + p.g[l], e.a = ws + p.a[l];
+    e.h = res ? ws + p.h[l] : nullptr;
+    if (l == p.L) {
+      e.wout = n.wout, e.delta = ws + p.delta[l], e.s = with_grad ? ws + p.szz[l] : nullptr;
+    }
+    e.ld = p.H[l], e.act = act;
+    int rc = dense<true, true>(s, g, e, 1, st, "F");
+    if (rc) return rc;
+  }
+  {
+    const long long thr = p.rows * 32;
+    head_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(ws + p.h[p.L], p.H[p.L], p.H[p.L], n.wout, n.bout, p.rows, ws + p.Y);
+    LAUNCH_CHECK("head");
+  }
+  for (int l = p.L; l >= 2; --l) {
+    GemmArgs g{};
+    g.M = R, g.N = p.H[l - 1], g.Nb = p.H[l - 1], g.kchunk = 0, g.nseg = 1;
+    g.seg[0] = GemmSeg{ws + p.delta[l], n.W[l], p.H[l], p.H[l - 1], p.H[l]};
+    EpiAdj e{};
+    e.a = ws + p.a[l - 1], e.g = ws + p.g[l - 1];
+    if (p.nais) {
+      if (l == p.L) e.res_head = n.wout; else e.res = ws + p.ht[l];
+      e.ht_out = (l - 1 >= 2) ? ws + p.ht[l - 1] : nullptr;
+    }
+    e.delta = ws + p.delta[l - 1];
+    e.s = with_grad ? ws + p.szz[l - 1] : nullptr;
+    e.ld = p.H[l - 1], e.act = act;
+    int rc = dense<true, false>(s, g, e, 1, st, "A");
+    if (rc) return rc;
+  }
+  {
+    GemmArgs g{};
+    g.M = R, g.N = p.ldx, g.Nb = p.d_in, g.kchunk = 0;
+    g.nseg = 1;
+    g.seg[0] = GemmSeg{ws + p.delta[1], n.W[1], p.H[1], p.d_in, p.H[1]};
+    if (p.nais)
+      for (int l = 2; l <= p.L; ++l) g.seg[g.nseg++] = GemmSeg{ws + p.delta[l], n.Win[l], p.H[l], p.d_in, p.H[l]};
+    int rc = dense<true, false>(s, g, EpiStore{ws + p.zf, p.ldx}, 1, st, "Du");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int run_loss(const FbsnnSpec* s, const Plan& p, float* ws, bool with_grad, float* loss_out, float* ybsum_out, cudaStream_t st) {
+  const ProblemK k = problem_k(s, p);
+  LossArgs a{};
+  a.xin = ws + p.xin, a.zf = ws + p.zf, a.sdw = ws + p.sdw, a.Y = ws + p.Y, a.rows = p.rows;
+  a.ev = ws + p.ev, a.part = ws + p.part_loss;
+  a.ybar = with_grad ? ws + p.ybar : nullptr, a.V = with_grad ? ws + p.V : nullptr;
+  loss_residual_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a);
+  LAUNCH_CHECK("loss_residual");
+  if (with_grad) {
+    loss_seed_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a);
+    LAUNCH_CHECK("loss_seed");
+  }
+  final_sum2_kernel<<<1, 1024, 0, st>>>(ws + p.part_loss, p.loss_blocks, FinalSum2{loss_out, with_grad ? ybsum_out : nullptr});
+  LAUNCH_CHECK("final_sum2");
+  return 0;
+}
+
+static int wgrad(const FbsnnSpec* s, const Plan& p, float* ws, const float* P0, const float* Q0, const float* P1,
+                 const float* Q1, int out, int in_pad, int in_valid, int ldq, float* dst, int ld_dst, cudaStream_t st) {
+  GemmArgs g{};
+  g.M = out, g.N = in_pad, g.Nb = in_pad, g.kchunk = p.wg_chunk, g.nseg = 2;
+  g.seg[0] = GemmSeg{P0, Q0, out, ldq, (int)p.rows};
+  g.seg[1] = GemmSeg{P1, Q1, out, ldq, (int)p.rows};
+  int rc = dense<false, false>(s, g, EpiPartial{ws + p.part_wg, out, in_pad}, p.wg_split, st, "G");
+  if (rc) return rc;
+  const int n = out * in_pad;
+  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws + p.part_wg, p.wg_split, out, in_pad, in_valid, dst, ld_dst);
+  LAUNCH_CHECK("reduce_partials");
+  return 0;
+}
+
+static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, float* grads, cudaStream_t st) {
+  const int R = (int)p.rows;
+  // ---- T sweep -----------------------------------------------------------------------------------------
+  for (int l = 1; l <= p.L; ++l) {
+    GemmArgs g{};
+    g.M = R, g.N = p.H[l], g.Nb = p.H[l], g.kchunk = 0;
+    if (l == 1) {
+      g.nseg = 1;
+      g.seg[0] = GemmSeg{ws + p.V, n.W[1], p.ldx, p.d_in, p.d_in};
+    } else {
+      g.nseg = 1;
+      g.seg[0] = GemmSeg{ws + p.hd[l - 1], n.W[l], p.H[l - 1], p.H[l - 1], p.H[l - 1]};
+      if (p.nais) {
+        g.nseg = 2;
+        g.seg[1] = GemmSeg{ws + p.V, n.Win[l], p.ldx, p.d_in, p.d_in};
+      }
+    }
+    EpiTan e{};
+    e.a = ws + p.a[l], e.s_zz = ws + p.szz[l];
+    e.res = (p.nais && l >= 2) ? ws + p.hd[l - 1] : nullptr;
+    e.hd = ws + p.hd[l];
+    if (l == p.L) e.ybar = ws + p.ybar, e.wout = n.wout;
+    e.ld = p.H[l];
+    int rc = dense<true, true>(s, g, e, 1, st, "T");
+    if (rc) return rc;
+  }
+  // ---- B sweep -----------------------------------------------------------------------------------------
+  for (int l = p.L; l >= 2; --l) {
+    GemmArgs g{};
+    g.M = R, g.N = p.H[l - 1], g.Nb = p.H[l - 1], g.kchunk = 0, g.nseg = 1;
+    g.seg[0] = GemmSeg{ws + p.szz[l], n.W[l], p.H[l], p.H[l - 1], p.H[l]};
+    EpiBwd e{};
+    e.a = ws + p.a[l - 1], e.zz_zbar = ws + p.szz[l - 1];
+    if (p.nais) {
+      if (l == p.L) e.ybar = ws + p.ybar, e.wout = n.wout; else e.res = ws + p.hb[l];
+      e.hb_out = (l - 1 >= 2) ? ws + p.hb[l - 1] : nullptr;
+    }
+    e.ld = p.H[l - 1];
+    int rc = dense<true, false>(s, g, e, 1, st, "B");
+    if (rc) return rc;
+  }
+  // ---- G contractions ------------------------------------------------------------------------------------
+  for (int l = 1; l <= p.L; ++l) {
+    int rc;
+    if (l == 1) {
+      rc = wgrad(s, p, ws, ws + p.szz[1], ws + p.xin, ws + p.delta[1], ws + p.V, p.H[1], p.ldx, p.d_in, p.ldx,
+                 grads + s->off_W[1], p.d_in, st);
+      if (rc) return rc;
+      continue;
+    }
+    float* dst = p.nais ? ws + p.Bbar[l] : grads + s->off_W[l];
+    rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.h[l - 1], ws + p.delta[l], ws + p.hd[l - 1], p.H[l], p.H[l - 1],
+               p.H[l - 1], p.H[l - 1], dst, p.H[l - 1], st);
+    if (rc) return rc;
+    if (p.nais) {
+      rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.xin, ws + p.delta[l], ws + p.V, p.H[l], p.ldx, p.d_in, p.ldx,
+                 grads + s->off_Win[l], p.d_in, st);
+      if (rc) return rc;
+      const int H = p.H[l];
+      nais_project_bwd_kernel<<<1, 1024, 0, st>>>(ws + p.Bbar[l], ws + p.Rm[l], H, ws + p.nstate[l], ws + p.Sm[l]);
+      LAUNCH_CHECK("nais_project_bwd");
+      GemmArgs g{};
+      g.M = H, g.N = H, g.Nb = H, g.kchunk = 0, g.nseg = 1;
+      g.seg[0] = GemmSeg{n.Wraw[l], ws + p.Sm[l], H, H, H};
+      rc = dense<true, false>(s, g, EpiStore{grads + s->off_W[l], H}, 1, st, "nais Wbar");
+      if (rc) return rc;
+    }
+  }
+  // ---- bias / output-layer gradients: column sums -----------------------------------------------------------
+  ColJobs js{};
+  js.rows = p.rows, js.rows_per_block = p.col_rows_per_block, js.max_width = 1024, js.part = ws + p.part_col;
+  int maxw = 0;
+  for (int l = 1; l <= p.L; ++l) {
+    ColJob& j = js.job[js.njobs++];
+    j.A = ws + p.szz[l], j.B = nullptr, j.y = nullptr;
+    j.out = grads + s->off_b[l];
+    j.out2 = (p.nais && l >= 2) ? grads + s->off_bin[l] : nullptr;
+    j.ld = p.H[l], j.width = p.H[l];
+    maxw = std::max(maxw, p.H[l]);
+  }
+  {
+    ColJob& j = js.job[js.njobs++];
+    j.A = ws + p.hd[p.L], j.B = ws + p.h[p.L], j.y = ws + p.ybar;
+    j.out = grads + s->off_W[p.L + 1], j.out2 = nullptr;
+    j.ld = p.H[p.L], j.width = p.H[p.L];
+  }
+  if (maxw > 1024) return fail(FBSNN_E_UNSUPPORTED, "hidden width %d > 1024", maxw);
+  colsum_stage1_kernel<<<dim3(p.col_blocks, js.njobs), 256, 0, st>>>(js);
+  LAUNCH_CHECK("colsum1");
+  colsum_stage2_kernel<<<dim3((maxw + 255) / 256, js.njobs), 256, 0, st>>>(js, p.col_blocks);
+  LAUNCH_CHECK("colsum2");
+  return 0;
+}
+
+static int check_ws(const Plan& p, const void* ws, size_t bytes) {
+  if (!ws) return fail(FBSNN_E_WORKSPACE, "workspace is null");
+  if (((uintptr_t)ws & 255) != 0) return fail(FBSNN_E_WORKSPACE, "workspace must be 256-byte aligned");
+  if (bytes < p.total * sizeof(float))
+    return fail(FBSNN_E_WORKSPACE, "workspace too small: %zu < %zu bytes", bytes, p.total * sizeof(float));
+  return 0;
+}
+
+static int gen_increments(const FbsnnSpec* s, const Plan& p, float* ws, long long M, float T, long long path_offset,
+                          uint64_t seed, uint64_t iteration, const long long* iter_dev, const float* chol,
+                          cudaStream_t st) {
+  const float sqrt_dt = (float)sqrt((double)T / (double)s->N);
+  const long long total = M * (long long)(s->N + 1) * ((s->D + 3) / 4);
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)num_sms() * 32);
+  float* target = chol ? ws + p.zraw : ws + p.inc;
+  brownian_increments_kernel<<<blocks, 256, 0, st>>>(target, M, s->N, s->D, sqrt_dt, p.ldi, path_offset, seed,
+                                                     iteration, iter_dev);
+  LAUNCH_CHECK("brownian_increments");
+  if (chol) {  // inc[r, i] = sum_j zraw[r, j] * L[i][j]   (np.einsum('ij,mnj->mni'), with_corr...:339-341)
+    GemmArgs g{};
+    g.M = (int)p.rows, g.N = p.ldi, g.Nb = s->D, g.kchunk = 0, g.nseg = 1;
+    g.seg[0] = GemmSeg{ws + p.zraw, chol, p.ldi, s->D, s->D};
+    int rc = dense<true, true>(s, g, EpiStore{ws + p.inc, p.ldi}, 1, st, "chol");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int loss_grad_impl(const FbsnnSpec* s, const float* params, float* grads, const float* t, const float* W,
+                          const float* Xi, int64_t xi_rows, int64_t M, float T, int64_t path_offset, uint64_t seed,
+                          uint64_t iteration, const long long* iter_dev, const float* chol, void* workspace,
+                          size_t wbytes, float* X_out, float* Y_out, float* Z_out, float* loss_out, bool with_grad,
+                          cudaStream_t st) {
+  int rc = validate(s);
+  if (rc) return rc;
+  if (!params || !Xi || M < 1 || (xi_rows != 1 && xi_rows != M)) return fail(FBSNN_E_BADARG, "bad params/Xi/M/xi_rows");
+  if (with_grad && !grads) return fail(FBSNN_E_BADARG, "grads is null");
+  if (W && !t) return fail(FBSNN_E_BADARG, "t is required with host-supplied W");
+  if (!W && !with_grad) return fail(FBSNN_E_BADARG, "forward needs (t, W)");
+  const long long rows = (long long)M * (s->N + 1);
+  if (rows > 0x7fffffffLL / 4) return fail(FBSNN_E_UNSUPPORTED, "too many rows (%lld); shard the paths", rows);
+  Plan p;
+  make_plan(s, rows, with_grad, p);
+  rc = check_ws(p, workspace, wbytes);
+  if (rc) return rc;
+  float* ws = (float*)workspace;
+  const Net n = bind_net(s, p, params, ws);
+  if (p.nais && (rc = nais_prepare(s, p, n, ws, st))) return rc;
+  if (!W && (rc = gen_increments(s, p, ws, M, T, path_offset, seed, iteration, iter_dev, chol, st))) return rc;
+  {
+    const ProblemK k = problem_k(s, p);
+    PathArgs a{};
+    a.t = W ? t : nullptr, a.W = W, a.inc = W ? nullptr : ws + p.inc, a.ldi = p.ldi;
+    a.Xi = Xi, a.xi_rows = xi_rows, a.M = M, a.T = T;
+    a.xin = ws + p.xin, a.sdw = ws + p.sdw, a.X_out = X_out;
+    const long long thr = (long long)M * s->D;
+    path_advance_kernel<<<(unsigned)((thr + 127) / 128), 128, 0, st>>>(k, a);
+    LAUNCH_CHECK("path_advance");
+  }
+  if ((rc = sweeps_forward(s, p, n, ws, with_grad, st))) return rc;
+  float* ybsum = with_grad ? grads + s->off_b[p.L + 1] : nullptr;
+  if (loss_out || with_grad) {
+    if ((rc = run_loss(s, p, ws, with_grad, loss_out, ybsum, st))) return rc;
+  }
+  if (Y_out) CU_CHECK(cudaMemcpyAsync(Y_out, ws + p.Y, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (Z_out) {
+    const long long nz = rows * s->D;
+    gather_z_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(ws + p.zf, p.ldx, s->D, rows, Z_out);
+    LAUNCH_CHECK("gather_z");
+  }
+  if (with_grad && (rc = sweeps_backward(s, p, n, ws, grads, st))) return rc;
+  return 0;
+}
+
+static int adam_impl(const FbsnnAdam* hp, float* params, const float* grads, float* m, float* v, int64_t n,
+                     void* opt_state, float* gsq_part, int gsq_blocks, cudaStream_t st) {
+  if (!hp || !params || !grads || !m || !v || !opt_state || n < 1) return fail(FBSNN_E_BADARG, "adam: null argument");
+  gradsq_kernel<<<gsq_blocks, 256, 0, st>>>(grads, n, gsq_part);
+  LAUNCH_CHECK("gradsq");
+  opt_prepare_kernel<<<1, 256, 0, st>>>(gsq_part, gsq_blocks, *hp, (OptState*)opt_state);
+  LAUNCH_CHECK("opt_prepare");
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
+  adam_kernel<<<blocks, 256, 0, st>>>(params, grads, m, v, n, (float)hp->beta1, (float)hp->beta2, (float)hp->eps,
+                                      (const OptState*)opt_state);
+  LAUNCH_CHECK("adam");
+  return 0;
+}
+
+}  // namespace fbsnn
+
+using namespace fbsnn;
+
+extern "C" {
+
+const char* fbsnn_last_error(void) { return g_err; }
+int fbsnn_version(void) { return 100; }
+long long fbsnn_launch_count(void) { return g_launches; }
+void fbsnn_dense_timing(int enable) { g_timing = enable != 0; g_ntimed = 0; }
+// Sums the recorded dense-layer launches (caller has synchronised): out = {n_launches, total ms, total FLOPs,
+// n tcgen05 launches, tcgen05 ms, tcgen05 FLOPs}.
+int fbsnn_dense_timing_read(double* out6) {
+  if (!out6) return FBSNN_E_BADARG;
+  for (int i = 0; i < 6; ++i) out6[i] = 0;
+  for (int i = 0; i < g_ntimed; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ev0[i], g_ev1[i]) != cudaSuccess) return fail(FBSNN_E_CUDA, "event not complete");
+    out6[0] += 1, out6[1] += ms, out6[2] += g_flops[i];
+    if (g_timed_tc[i]) out6[3] += 1, out6[4] += ms, out6[5] += g_flops[i];
+  }
+  return 0;
+}
+
+int fbsnn_workspace_bytes(const FbsnnSpec* spec, int64_t n_paths, int with_grad, size_t* bytes_out) {
+  int rc = validate(spec);
+  if (rc) return rc;
+  if (n_paths < 1 || !bytes_out) return fail(FBSNN_E_BADARG, "n_paths < 1 or bytes_out null");
+  Plan p;
+  make_plan(spec, (long long)n_paths * (spec->N + 1), with_grad != 0, p);
+  *bytes_out = p.total * sizeof(float);
+  return 0;
+}
+
+int fbsnn_fetch_minibatch(const FbsnnSpec* spec, float T, int64_t n_paths, int64_t path_offset, uint64_t seed,
+                          uint64_t iteration, const float* chol, void* workspace, size_t workspace_bytes,
+                          float* t_out, float* W_out, void* stream) {
+  int rc = validate(spec);
+  if (rc) return rc;
+  if (n_paths < 1 || !W_out) return fail(FBSNN_E_BADARG, "n_paths < 1 or W_out null");
+  Plan p;
+  make_plan(spec, (long long)n_paths * (spec->N + 1), true, p);
+  if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  if ((rc = gen_increments(spec, p, ws, n_paths, T, path_offset, seed, iteration, nullptr, chol, st))) return rc;
+  const long long thr = (long long)n_paths * spec->D;
+  cumsum_paths_kernel<<<(unsigned)((thr + 127) / 128), 128, 0, st>>>(ws + p.inc, p.ldi, W_out, t_out, n_paths, spec->N, spec->D, T);
+  LAUNCH_CHECK("cumsum_paths");
+  return 0;
+}
+
+int fbsnn_net_u(const FbsnnSpec* spec, const float* params, const float* t, const float* X, int64_t rows,
+                void* workspace, size_t workspace_bytes, float* u_out, float* du_out, void* stream) {
+  int rc = validate(spec);
+  if (rc) return rc;
+  if (!params || !t || !X || rows < 1) return fail(FBSNN_E_BADARG, "net_u: null argument");
+  Plan p;
+  make_plan(spec, rows, false, p);
+  if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  const Net n = bind_net(spec, p, params, ws);
+  if (p.nais && (rc = nais_prepare(spec, p, n, ws, st))) return rc;
+  const long long tot = rows * p.ldx;
+  pack_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(t, X, rows, spec->D, p.ldx, ws + p.xin);
+  LAUNCH_CHECK("pack_rows");
+  if ((rc = sweeps_forward(spec, p, n, ws, false, st))) return rc;
+  if (u_out) CU_CHECK(cudaMemcpyAsync(u_out, ws + p.Y, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (du_out) {
+    const long long nz = rows * spec->D;
+    gather_z_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(ws + p.zf, p.ldx, spec->D, rows, du_out);
+    LAUNCH_CHECK("gather_z");
+  }
+  return 0;
+}
+
+int fbsnn_forward(const FbsnnSpec* spec, const float* params, const float* t, const float* W, const float* Xi,
+                  int64_t xi_rows, int64_t n_paths, void* workspace, size_t workspace_bytes, float* X_out,
+                  float* Y_out, float* Z_out, float* loss_out, void* stream) {
+  return loss_grad_impl(spec, params, nullptr, t, W, Xi, xi_rows, n_paths, 0.f, 0, 0, 0, nullptr, nullptr, workspace,
+                        workspace_bytes, X_out, Y_out, Z_out, loss_out, false, (cudaStream_t)stream);
+}
+
+int fbsnn_loss_grad(const FbsnnSpec* spec, const float* params, float* grads, const float* t, const float* W,
+                    const float* Xi, int64_t xi_rows, int64_t n_paths, float T, int64_t path_offset,
+                    uint64_t seed, uint64_t iteration, const float* chol, void* workspace,
+                    size_t workspace_bytes, float* X_out, float* Y_out, float* Z_out, float* loss_out,
+                    void* stream) {
+  return loss_grad_impl(spec, params, grads, t, W, Xi, xi_rows, n_paths, T, path_offset, seed, iteration, nullptr,
+                        chol, workspace, workspace_bytes, X_out, Y_out, Z_out, loss_out, true, (cudaStream_t)stream);
+}
+
+int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads, float* exp_avg,
+                    float* exp_avg_sq, int64_t n_params, void* opt_state, void* stream) {
+  // scratch for the squared-norm partials lives behind the 64-byte state block (FBSNN_OPT_STATE_BYTES)
+  return adam_impl(host_hp, params, grads, exp_avg, exp_avg_sq, n_params, opt_state,
+                   (float*)((char*)opt_state + 64), 256, (cudaStream_t)stream);
+}
+
+int fbsnn_train_step(const FbsnnSpec* spec, const FbsnnAdam* host_hp, float* params, float* grads,
+                     float* exp_avg, float* exp_avg_sq, void* opt_state, const float* t, const float* W,
+                     const float* Xi, int64_t xi_rows, int64_t n_paths, float T, int64_t path_offset,
+                     uint64_t seed, uint64_t iteration, const float* chol, void* workspace,
+                     size_t workspace_bytes, float* X_out, float* Y_out, float* loss_out, void* stream) {
+  if (!opt_state) return fail(FBSNN_E_BADARG, "opt_state is null");
+  int rc = loss_grad_impl(spec, params, grads, t, W, Xi, xi_rows, n_paths, T, path_offset, seed, iteration,
+                          (const long long*)opt_state, chol, workspace, workspace_bytes, X_out, Y_out, nullptr,
+                          loss_out, true, (cudaStream_t)stream);
+  if (rc) return rc;
+  return adam_impl(host_hp, params, grads, exp_avg, exp_avg_sq, spec->n_params, opt_state,
+                   (float*)((char*)opt_state + 64), 256, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// fp32 SIMT GEMM with fused sweep epilogues (the FBSNN_PREC_FP32 arithmetic variant).
+//
+//   C[M x N] = sum over segments s of  A_s[M x K_s] * B_s[K_s x N]        (up to 4 K-concatenated segments)
+//
+// Operand layouts (template flags):
+//   A_KC: A[m*lda + k] (k contiguous: activation rows)      !A_KC: A[k*lda + m] (weight-gradient operand P^T)
+//   B_KC: B[n*ldb + k] (PyTorch (out,in) weight used as W^T) !B_KC: B[k*ldb + n] (weight used as W, or rows x in)
+// Split-K (weight gradients): blockIdx.z selects rows [z*kchunk, (z+1)*kchunk) of every segment and the
+// epilogue stores a partial tile; a deterministic second pass sums the partials (no atomics anywhere).
+// All output widths N and leading dimensions of epilogue arrays are multiples of 4 (float4 epilogue I/O).
+#pragma once
+#include "common.cuh"
+
+namespace fbsnn {
+
+struct GemmSeg {
+  const float* A;
+  const float* B;
+  int lda, ldb, K;
+};
+struct GemmArgs {
+  GemmSeg seg[4];
+  int nseg;
+  int M, N;
+  int Nb;      // valid columns of the B operands (<= N; columns in [Nb, N) read as zero)
+  int kchunk;  // 0: no split-K
+};
+
+// ----------------------------------------------------------------------------------------------------
+// epilogues: operator()(row, col, acc4) with col % 4 == 0 and col + 3 < N
+// ----------------------------------------------------------------------------------------------------
+// F sweep: z = acc + bias;  g = act(z), a = act'(z);  h = g (+ h_prev);  last layer also seeds the adjoint
+struct EpiFwd {
+  const float* bias1;
+  const float* bias2;  // nullable (NAIS: layer{l}_input.bias)
+  const float* res;    // nullable: h_{l-1} (NAIS residual stream)
+  float* g;
+  float* a;
+  float* h;            // nullable (only with res)
+  const float* wout;   // nullable: last hidden layer -> delta = wout * a, s = wout * c
+  float* delta;
+  float* s;            // nullable (forward-only mode)
+  int ld, act;
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+    const float4 b1 = ld4(bias1 + c);
+    float z[4] = {v.x + b1.x, v.y + b1.y, v.z + b1.z, v.w + b1.w};
+    if (bias2) {
+      const float4 b2 = ld4(bias2 + c);
+      z[0] += b2.x, z[1] += b2.y, z[2] += b2.z, z[3] += b2.w;
+    }
+    float gv[4], av[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) act_ga(act, z[i], gv[i], av[i]);
+    const size_t o = (size_t)r * ld + c;
+    st4(g + o, make_float4(gv[0], gv[1], gv[2], gv[3]));
+    st4(a + o, make_float4(av[0], av[1], av[2], av[3]));
+    if (h) {
+      const float4 p = ld4(res + o);
+      st4(h + o, make_float4(gv[0] + p.x, gv[1] + p.y, gv[2] + p.z, gv[3] + p.w));
+    }
+    if (wout) {
+      const float4 w = ld4(wout + c);
+      st4(delta + o, make_float4(w.x * av[0], w.y * av[1], w.z * av[2], w.w * av[3]));
+      if (s)
+        st4(s + o, make_float4(w.x * act_c(act, gv[0], av[0]), w.y * act_c(act, gv[1], av[1]),
+                               w.z * act_c(act, gv[2], av[2]), w.w * act_c(act, gv[3], av[3])));
+    }
+  }
+};
+
+// A sweep (writes layer l-1): ht = acc (+ ht_l | + wout);  delta = ht * a;  s = ht * c
+struct EpiAdj {
+  const float* a;
+  const float* g;
+  const float* res;       // nullable: ht_l (NAIS)
+  const float* res_head;  // nullable: ht_L = wout broadcast over rows (NAIS, l = L)
+  float* ht_out;          // nullable
+  float* delta;
+  float* s;               // nullable (forward-only mode)
+  int ld, act;
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+    const size_t o = (size_t)r * ld + c;
+    float ht[4] = {v.x, v.y, v.z, v.w};
+    if (res) {
+      const float4 p = ld4(res + o);
+      ht[0] += p.x, ht[1] += p.y, ht[2] += p.z, ht[3] += p.w;
+    } else if (res_head) {
+      const float4 p = ld4(res_head + c);
+      ht[0] += p.x, ht[1] += p.y, ht[2] += p.z, ht[3] += p.w;
+    }
+    const float4 av = ld4(a + o);
+    st4(delta + o, make_float4(ht[0] * av.x, ht[1] * av.y, ht[2] * av.z, ht[3] * av.w));
+    if (s) {
+      const float4 gv = ld4(g + o);
+      st4(s + o, make_float4(ht[0] * act_c(act, gv.x, av.x), ht[1] * act_c(act, gv.y, av.y),
+                             ht[2] * act_c(act, gv.z, av.z), ht[3] * act_c(act, gv.w, av.w)));
+    }
+    if (ht_out) st4(ht_out + o, make_float4(ht[0], ht[1], ht[2], ht[3]));
+  }
+};
+
+// T sweep (layer l): dbar = acc;  hd = dbar * a (+ hd_{l-1});  zz = dbar * s;  last layer: zbar = ybar*wout*a + zz
+struct EpiTan {
+  const float* a;
+  float* s_zz;        // in: s, out: zz (or zbar for the last layer)
+  const float* res;   // nullable: hd_{l-1}
+  float* hd;
+  const float* ybar;  // nullable: last layer
+  const float* wout;
+  int ld;
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+    const size_t o = (size_t)r * ld + c;
+    const float4 av = ld4(a + o);
+    const float4 sv = ld4(s_zz + o);
+    float hdv[4] = {v.x * av.x, v.y * av.y, v.z * av.z, v.w * av.w};
+    float zz[4] = {v.x * sv.x, v.y * sv.y, v.z * sv.z, v.w * sv.w};
+    if (res) {
+      const float4 p = ld4(res + o);
+      hdv[0] += p.x, hdv[1] += p.y, hdv[2] += p.z, hdv[3] += p.w;
+    }
+    if (wout) {
+      const float yb = ybar[r];
+      const float4 w = ld4(wout + c);
+      zz[0] += yb * w.x * av.x, zz[1] += yb * w.y * av.y, zz[2] += yb * w.z * av.z, zz[3] += yb * w.w * av.w;
+    }
+    st4(hd + o, make_float4(hdv[0], hdv[1], hdv[2], hdv[3]));
+    st4(s_zz + o, make_float4(zz[0], zz[1], zz[2], zz[3]));
+  }
+};
+
+// B sweep (writes layer l-1): hb = acc (+ hb_l | + ybar*wout);  zbar = hb * a + zz
+struct EpiBwd {
+  const float* a;
+  float* zz_zbar;
+  const float* res;   // nullable: hb_l (NAIS, l < L)
+  const float* ybar;  // nullable: NAIS l = L, residual is ybar[r] * wout[c]
+  const float* wout;
+  float* hb_out;      // nullable
+  int ld;
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+    const size_t o = (size_t)r * ld + c;
+    float hb[4] = {v.x, v.y, v.z, v.w};
+    if (res) {
+      const float4 p = ld4(res + o);
+      hb[0] += p.x, hb[1] += p.y, hb[2] += p.z, hb[3] += p.w;
+    } else if (ybar) {
+      const float yb = ybar[r];
+      const float4 w = ld4(wout + c);
+      hb[0] += yb * w.x, hb[1] += yb * w.y, hb[2] += yb * w.z, hb[3] += yb * w.w;
+    }
+    const float4 av = ld4(a + o);
+    const float4 zz = ld4(zz_zbar + o);
+    st4(zz_zbar + o, make_float4(hb[0] * av.x + zz.x, hb[1] * av.y + zz.y, hb[2] * av.z + zz.z, hb[3] * av.w + zz.w));
+    if (hb_out) st4(hb_out + o, make_float4(hb[0], hb[1], hb[2], hb[3]));
+  }
+};
+
+struct EpiStore {
+  float* out;
+  int ld;
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const { st4(out + (size_t)r * ld + c, v); }
+};
+
+// split-K partial tile: out[z][M][N]
+struct EpiPartial {
+  float* out;
+  int M, N;
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+    st4(out + ((size_t)blockIdx.z * M + r) * N + c, v);
+  }
+};
+
+// ----------------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int TM, int TN, bool A_KC, bool B_KC, class Epi>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), (BM >= 128 ? 2 : 3))
+gemm_simt_kernel(const GemmArgs g, const Epi epi) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int A_LD = BM * BK / NT, B_LD = BN * BK / NT;
+  constexpr int GM = 4 * BM / TM, GN = 4 * BN / TN;  // row / column stride between a thread's 4-wide groups
+  static_assert(TM % 4 == 0 && TN % 4 == 0 && (BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile shape");
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float ra[A_LD], rb[B_LD];
+
+  auto kbeg = [&](int s) { return g.kchunk ? (int)min((long long)g.seg[s].K, (long long)blockIdx.z * g.kchunk) : 0; };
+  auto kend = [&](int s) {
+    return g.kchunk ? (int)min((long long)g.seg[s].K, ((long long)blockIdx.z + 1) * g.kchunk) : g.seg[s].K;
+  };
+  auto gload = [&](int s, int k0, int ke) {
+    const float* __restrict__ A = g.seg[s].A;
+    const float* __restrict__ B = g.seg[s].B;
+    const int lda = g.seg[s].lda, ldb = g.seg[s].ldb;
+#pragma unroll
+    for (int p = 0; p < A_LD; ++p) {
+      const int e = tid + p * NT;
+      int m, k;
+      if (A_KC) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < g.M && gk < ke) v = A_KC ? __ldg(A + (size_t)gm * lda + gk) : __ldg(A + (size_t)gk * lda + gm);
+      ra[p] = v;
+    }
+#pragma unroll
+    for (int p = 0; p < B_LD; ++p) {
+      const int e = tid + p * NT;
+      int n, k;
+      if (B_KC) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < g.Nb && gk < ke) v = B_KC ? __ldg(B + (size_t)gn * ldb + gk) : __ldg(B + (size_t)gk * ldb + gn);
+      rb[p] = v;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int p = 0; p < A_LD; ++p) {
+      const int e = tid + p * NT;
+      int m, k;
+      if (A_KC) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+      As[buf][k][m] = ra[p];
+    }
+#pragma unroll
+    for (int p = 0; p < B_LD; ++p) {
+      const int e = tid + p * NT;
+      int n, k;
+      if (B_KC) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      Bs[buf][k][n] = rb[p];
+    }
+  };
+
+  // first non-empty segment
+  int s = 0;
+  while (s < g.nseg && kbeg(s) >= kend(s)) ++s;
+  if (s < g.nseg) {
+    int k0 = kbeg(s), ke = kend(s);
+    gload(s, k0, ke);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    while (true) {
+      int ns = s, nk0 = k0 + BK, nke = ke;
+      if (nk0 >= ke) {
+        ++ns;
+        while (ns < g.nseg && kbeg(ns) >= kend(ns)) ++ns;
+        if (ns < g.nseg) { nk0 = kbeg(ns); nke = kend(ns); }
+      }
+      const bool more = ns < g.nseg;
+      if (more) gload(ns, nk0, nke);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float av[TM], bv[TN];
+#pragma unroll
+        for (int i4 = 0; i4 < TM / 4; ++i4) {
+          const float4 t = ld4(&As[buf][kk][i4 * GM + ty * 4]);
+          av[i4 * 4 + 0] = t.x, av[i4 * 4 + 1] = t.y, av[i4 * 4 + 2] = t.z, av[i4 * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < TN / 4; ++j4) {
+          const float4 t = ld4(&Bs[buf][kk][j4 * GN + tx * 4]);
+          bv[j4 * 4 + 0] = t.x, bv[j4 * 4 + 1] = t.y, bv[j4 * 4 + 2] = t.z, bv[j4 * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (!more) break;
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+      s = ns, k0 = nk0, ke = nke;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int r = m0 + (i / 4) * GM + ty * 4 + (i % 4);
+    if (r >= g.M) continue;
+#pragma unroll
+    for (int j4 = 0; j4 < TN / 4; ++j4) {
+      const int c = n0 + j4 * GN + tx * 4;
+      if (c < g.N) epi(r, c, make_float4(acc[i][j4 * 4 + 0], acc[i][j4 * 4 + 1], acc[i][j4 * 4 + 2], acc[i][j4 * 4 + 3]));
+    }
+  }
+}
+
+// Host launcher: picks the 128x128 (8x8 micro-tile) shape when the grid fills the chip at least twice,
+// else 64x64 (4x4) so that small-M steps still spread over all 148 SMs.
+template <bool A_KC, bool B_KC, class Epi>
+inline cudaError_t launch_gemm(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
+  const long long big_ctas = (long long)((g.M + 127) / 128) * ((g.N + 127) / 128) * nsplit;
+  if (big_ctas >= 2LL * num_sms) {
+    dim3 grid((g.M + 127) / 128, (g.N + 127) / 128, nsplit);
+    gemm_simt_kernel<128, 128, 16, 8, 8, A_KC, B_KC, Epi><<<grid, 256, 0, st>>>(g, epi);
+  } else {
+    dim3 grid((g.M + 63) / 64, (g.N + 63) / 64, nsplit);
+    gemm_simt_kernel<64, 64, 16, 4, 4, A_KC, B_KC, Epi><<<grid, 256, 0, st>>>(g, epi);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fbsnn

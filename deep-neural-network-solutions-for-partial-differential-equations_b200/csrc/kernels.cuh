@@ -1,0 +1,456 @@
+// Element-wise and reduction kernels of the FBSNN step: Brownian increments, Euler-Maruyama path advance,
+// output head, residual loss and its seeds, column sums, split-K reduction, NAIS projection, clip + Adam.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace fbsnn {
+
+// Problem constants handed to the path / loss kernels (closed enumeration).
+struct ProblemK {
+  int D, N, ldx;
+  int mu_kind, sigma_kind, phi_kind, g_kind;
+  float mu_c, sigma_c, phi_c, strike;
+};
+
+// ----------------------------------------------------------------------------------------------------
+// Brownian increments  (replaces np.random.normal + sqrt(dt) scaling of FBSNN.fetch_minibatch,
+// DeepBSDE.py:252-255).  One Philox block -> 4 normals for 4 consecutive dimensions of one (path, step).
+// Layout: inc[(m*(N+1) + n)*ldi + d] = increment from step n-1 to n  (row 0 is zero, like the reference DW).
+// ----------------------------------------------------------------------------------------------------
+__global__ void brownian_increments_kernel(float* __restrict__ inc, long long M, int N, int D, float sqrt_dt,
+                                           int ldi, long long path_offset, uint64_t seed, uint64_t iteration,
+                                           const long long* __restrict__ iter_dev) {
+  // iter_dev (nullable): device-resident counter added to `iteration`, so that a captured CUDA graph draws a
+  // fresh stream on every replay (the optimiser step counter is used for this).
+  if (iter_dev) iteration += (uint64_t)iter_dev[0];
+  const int D4 = (D + 3) / 4;
+  const long long total = M * (long long)(N + 1) * D4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d4 = (int)(i % D4);
+    const long long row = i / D4;
+    const int n = (int)(row % (N + 1));
+    const long long m = row / (N + 1);
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n > 0) {
+      const uint64_t gp = (uint64_t)(m + path_offset);
+      const Philox4 ctr{(uint32_t)gp, (uint32_t)(gp >> 32), (uint32_t)(n * D4 + d4), (uint32_t)iteration};
+      normal4(philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32)), z);
+    }
+    float* o = inc + row * ldi + d4 * 4;   // ldi % 4 == 0: columns [D, ldi) are zero padding
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (d4 * 4 + j >= D) z[j] = 0.f;
+    st4(o, make_float4(sqrt_dt * z[0], sqrt_dt * z[1], sqrt_dt * z[2], sqrt_dt * z[3]));
+  }
+}
+
+// cumulative (t, W) in the reference's layout from increments (np.cumsum, DeepBSDE.py:257-258).
+// One thread per (path, dim), sequential prefix sum along n.
+__global__ void cumsum_paths_kernel(const float* inc, int ldi, float* W, float* t, long long M, int N, int D,
+                                    float T) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= M * D) return;
+  const long long m = idx / D;
+  const int d = (int)(idx % D);
+  float acc = 0.f;
+  for (int n = 0; n <= N; ++n) {
+    const long long r = m * (N + 1) + n;
+    acc += inc[r * ldi + d];
+    W[r * D + d] = acc;
+    if (t && d == 0) t[r] = (float)((double)n * (double)T / (double)N);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Euler-Maruyama path advance (X recursion of FBSNN.loss_function, DeepBSDE.py:218-222).
+// One thread per (path, dim), sequential over n.  Writes the network input rows xin = [t, X, 0-pad],
+// sdw[row n] = sigma(X_n) dW_n (consumed by the loss kernels) and optionally X in the reference layout.
+// Arithmetic order follows the reference exactly: X1 = (X0 + (mu_c*X0)*(t1-t0)) + (sigma*X0)*dW, no FMA
+// contraction, dW and dt re-differenced in fp32 from the cumulative inputs.
+// ----------------------------------------------------------------------------------------------------
+struct PathArgs {
+  const float* t;      // (M, N+1) or null (uniform grid n*T/N)
+  const float* W;      // cumulative (M, N+1, D) or null
+  const float* inc;    // increments (M, N+1, ldi) (row n = step n-1 -> n), used when W is null
+  int ldi;
+  const float* Xi;
+  long long xi_rows, M;
+  float T;
+  float* xin;
+  float* sdw;
+  float* X_out;  // nullable
+};
+
+__global__ void path_advance_kernel(const ProblemK p, const PathArgs a) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= a.M * p.D) return;
+  const long long m = idx / p.D;
+  const int d = (int)(idx % p.D);
+  const int N = p.N, D = p.D, ldx = p.ldx;
+  float x = a.Xi[(a.xi_rows == 1 ? 0 : m) * D + d];
+  const long long row0 = m * (N + 1);
+  float tn = a.t ? a.t[row0] : 0.f;
+  float wn = a.W ? a.W[row0 * D + d] : 0.f;
+  for (int n = 0; n <= N; ++n) {
+    const long long r = row0 + n;
+    float* xr = a.xin + r * ldx;
+    xr[1 + d] = x;
+    if (d == 0) {
+      xr[0] = tn;
+      for (int c = D + 1; c < ldx; ++c) xr[c] = 0.f;
+    }
+    if (a.X_out) a.X_out[r * D + d] = x;
+    if (n == N) break;
+    const float tn1 = a.t ? a.t[r + 1] : (float)((double)(n + 1) * (double)a.T / (double)N);
+    const float dt = __fsub_rn(tn1, tn);
+    float dw;
+    if (a.W) {
+      const float wn1 = a.W[(r + 1) * D + d];
+      dw = __fsub_rn(wn1, wn);
+      wn = wn1;
+    } else {
+      dw = a.inc[(r + 1) * a.ldi + d];
+    }
+    const float sig = p.sigma_kind == FBSNN_SIGMA_PROP ? __fmul_rn(p.sigma_c, x) : p.sigma_c;
+    const float sd = __fmul_rn(sig, dw);
+    a.sdw[r * D + d] = sd;
+    const float mu = p.mu_kind == FBSNN_MU_LINEAR ? __fmul_rn(p.mu_c, x) : 0.f;
+    x = __fadd_rn(__fadd_rn(x, __fmul_rn(mu, dt)), sd);
+    tn = tn1;
+  }
+}
+
+// rows of arbitrary (t, X) for net_u: xin = [t, X, 0-pad]
+__global__ void pack_rows_kernel(const float* t, const float* X, long long rows, int D, int ldx, float* xin) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows * ldx) return;
+  const long long r = i / ldx;
+  const int c = (int)(i % ldx);
+  xin[i] = c == 0 ? t[r] : (c <= D ? X[r * D + c - 1] : 0.f);
+}
+
+// u[r] = h_L[r,:] . wout + bout      (one warp per row)
+__global__ void head_kernel(const float* __restrict__ h, int ld, int H, const float* __restrict__ wout,
+                            const float* __restrict__ bout, long long rows, float* __restrict__ u) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int c = lane; c < H; c += 32) acc = fmaf(h[r * ld + c], __ldg(wout + c), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) u[r] = acc + bout[0];
+}
+
+// copy column block [1, D] of ZF (rows, ldx) / scalar Y into user-visible outputs
+__global__ void gather_z_kernel(const float* __restrict__ zf, int ldx, int D, long long rows, float* __restrict__ Z) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  Z[i] = zf[(i / D) * ldx + 1 + (i % D)];
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Residual loss (FBSNN.loss_function, DeepBSDE.py:223-240) -- one warp per (path, step) row.
+//   n < N : e_n = Y_{n+1} - (Y_n + phi(X_n,Y_n,Z_n) dt + Z_n . sdw_n)
+//   n = N : e_N = Y_N - g(X_N)   and   sum_d (Z_N - grad g(X_N))^2
+// ev[r] keeps the residual for the seed kernel; per-block partial sums of squares go to loss_part.
+// ----------------------------------------------------------------------------------------------------
+struct LossArgs {
+  const float* xin;
+  const float* zf;
+  const float* sdw;
+  const float* Y;
+  long long rows;
+  float* ev;
+  float* ybar;
+  float* V;
+  float* part;   // [2][gridDim.x] partial sums: loss, sum(ybar)
+};
+
+__device__ __forceinline__ void terminal_g(const ProblemK& p, float sumx, float sumx2, float& g, float& dg_scale) {
+  // g(X_N) and the scalar s.t. grad g = dg_scale * X (sumsq, logq) or dg_scale * 1 (calls)
+  if (p.g_kind == FBSNN_G_SUMSQ) {
+    g = sumx2;
+    dg_scale = 2.f;
+  } else if (p.g_kind == FBSNN_G_LOGQ) {
+    const float q = 0.5f + 0.5f * sumx2;
+    g = logf(q);
+    dg_scale = 1.f / q;
+  } else {
+    const float base = p.g_kind == FBSNN_G_CALL_SUM ? sumx : sumx / (float)p.D;
+    const float sc = p.g_kind == FBSNN_G_CALL_SUM ? 1.f : 1.f / (float)p.D;
+    g = fmaxf(base - p.strike, 0.f);
+    dg_scale = base > p.strike ? sc : (base == p.strike ? 0.5f * sc : 0.f);  // torch.maximum splits ties
+  }
+}
+
+__global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
+  __shared__ float red[32];
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float contrib = 0.f;
+  if (r < a.rows) {
+    const int n = (int)(r % (p.N + 1));
+    const float* x = a.xin + r * p.ldx + 1;
+    const float* z = a.zf + r * p.ldx + 1;
+    if (n < p.N) {
+      const float* sd = a.sdw + r * p.D;
+      float zs = 0.f, xz = 0.f, z2 = 0.f;
+      for (int d = lane; d < p.D; d += 32) {
+        const float zv = z[d];
+        zs = fmaf(zv, sd[d], zs);
+        xz = fmaf(x[d], zv, xz);
+        z2 = fmaf(zv, zv, z2);
+      }
+      zs = warp_sum(zs), xz = warp_sum(xz), z2 = warp_sum(z2);
+      const float y = a.Y[r];
+      const float dt = a.xin[(r + 1) * p.ldx] - a.xin[r * p.ldx];
+      float phi;
+      if (p.phi_kind == FBSNN_PHI_BSB) phi = p.phi_c * (y - xz);
+      else if (p.phi_kind == FBSNN_PHI_RY) phi = p.phi_c * y;
+      else phi = z2;
+      const float e = a.Y[r + 1] - (y + phi * dt + zs);
+      if (lane == 0) { a.ev[r] = e; contrib = e * e; }
+    } else {
+      float sx = 0.f, sx2 = 0.f;
+      for (int d = lane; d < p.D; d += 32) { const float xv = x[d]; sx += xv; sx2 = fmaf(xv, xv, sx2); }
+      sx = warp_sum(sx), sx2 = warp_sum(sx2);
+      float g, dgs;
+      terminal_g(p, sx, sx2, g, dgs);
+      const bool mulx = p.g_kind == FBSNN_G_SUMSQ || p.g_kind == FBSNN_G_LOGQ;
+      float zt = 0.f;
+      for (int d = lane; d < p.D; d += 32) {
+        const float diff = z[d] - (mulx ? dgs * x[d] : dgs);
+        zt = fmaf(diff, diff, zt);
+      }
+      zt = warp_sum(zt);
+      const float e = a.Y[r] - g;
+      if (lane == 0) { a.ev[r] = e; contrib = e * e + zt; }
+    }
+  }
+  const float tot = block_sum(contrib, red);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = tot;
+}
+
+// Seeds of the reverse sweeps: ybar = dL/dY, V = [0, dL/dZ, 0-pad] per row.
+__global__ void loss_seed_kernel(const ProblemK p, const LossArgs a) {
+  __shared__ float red[32];
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float yb = 0.f;
+  if (r < a.rows) {
+    const int n = (int)(r % (p.N + 1));
+    const float* x = a.xin + r * p.ldx + 1;
+    const float* z = a.zf + r * p.ldx + 1;
+    float* v = a.V + r * p.ldx;
+    const float e = a.ev[r];
+    if (n < p.N) {
+      const float* sd = a.sdw + r * p.D;
+      const float dt = a.xin[(r + 1) * p.ldx] - a.xin[r * p.ldx];
+      const float phi_y = p.phi_kind == FBSNN_PHI_ZSQ ? 0.f : p.phi_c;
+      yb = -2.f * e * (1.f + phi_y * dt);
+      if (n > 0) yb += 2.f * a.ev[r - 1];
+      for (int d = lane; d < p.D; d += 32) {
+        float pz;
+        if (p.phi_kind == FBSNN_PHI_BSB) pz = -p.phi_c * x[d];
+        else if (p.phi_kind == FBSNN_PHI_RY) pz = 0.f;
+        else pz = 2.f * z[d];
+        v[1 + d] = -2.f * e * (pz * dt + sd[d]);
+      }
+    } else {
+      float sx = 0.f, sx2 = 0.f;
+      for (int d = lane; d < p.D; d += 32) { const float xv = x[d]; sx += xv; sx2 = fmaf(xv, xv, sx2); }
+      sx = warp_sum(sx), sx2 = warp_sum(sx2);
+      float g, dgs;
+      terminal_g(p, sx, sx2, g, dgs);
+      const bool mulx = p.g_kind == FBSNN_G_SUMSQ || p.g_kind == FBSNN_G_LOGQ;
+      yb = 2.f * e + (p.N > 0 ? 2.f * a.ev[r - 1] : 0.f);
+      for (int d = lane; d < p.D; d += 32) v[1 + d] = 2.f * (z[d] - (mulx ? dgs * x[d] : dgs));
+    }
+    if (lane == 0) {
+      v[0] = 0.f;
+      for (int c = p.D + 1; c < p.ldx; ++c) v[c] = 0.f;
+      a.ybar[r] = yb;
+    }
+  }
+  const float tot = block_sum(lane == 0 ? yb : 0.f, red);
+  if (threadIdx.x == 0) a.part[gridDim.x + blockIdx.x] = tot;
+}
+
+// out_j[0] = (float) sum_i part[j*n + i], j = 0,1   (single block, double accumulation, deterministic)
+struct FinalSum2 {
+  float* out0;
+  float* out1;
+};
+__global__ void final_sum2_kernel(const float* __restrict__ part, int n, FinalSum2 o) {
+  __shared__ double red[32];
+  for (int j = 0; j < 2; ++j) {
+    float* out = j == 0 ? o.out0 : o.out1;
+    if (!out) continue;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)part[(size_t)j * n + i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = (float)acc;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Column sums over rows (bias gradients, output-layer weight gradient), two deterministic stages.
+//   job j: out[c] = sum_r ( A[r*ld + c] + (B ? y[r] * B[r*ld + c] : 0) )
+// ----------------------------------------------------------------------------------------------------
+struct ColJob {
+  const float* A;
+  const float* B;   // nullable
+  const float* y;   // with B
+  float* out;       // final destination(s)
+  float* out2;      // nullable second destination (NAIS: layer{l}.bias and layer{l}_input.bias share a gradient)
+  int ld, width;
+};
+constexpr int kMaxColJobs = 12;
+struct ColJobs {
+  ColJob job[kMaxColJobs];
+  int njobs;
+  long long rows;
+  int rows_per_block;
+  int max_width;
+  float* part;  // [njobs][gridDim.x][max_width]
+};
+
+__global__ void colsum_stage1_kernel(const ColJobs js) {
+  const ColJob& j = js.job[blockIdx.y];
+  const long long r0 = (long long)blockIdx.x * js.rows_per_block;
+  const long long r1 = min(js.rows, r0 + js.rows_per_block);
+  for (int c = threadIdx.x; c < j.width; c += blockDim.x) {
+    float acc = 0.f;
+    if (j.B) {
+      for (long long r = r0; r < r1; ++r) acc += j.A[r * j.ld + c] + j.y[r] * j.B[r * j.ld + c];
+    } else {
+      for (long long r = r0; r < r1; ++r) acc += j.A[r * j.ld + c];
+    }
+    js.part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * js.max_width + c] = acc;
+  }
+}
+__global__ void colsum_stage2_kernel(const ColJobs js, int nblk) {
+  const ColJob& j = js.job[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= j.width) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += js.part[((size_t)blockIdx.y * nblk + b) * js.max_width + c];
+  j.out[c] = acc;
+  if (j.out2) j.out2[c] = acc;
+}
+
+// out[o*ld_out + i] = sum_z part[z][o][i_pad]   (weight-gradient split-K second stage)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nsplit, int rows, int cols_pad, int cols,
+                                       float* __restrict__ out, int ld_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols_pad) return;
+  const int o = idx / cols_pad, i = idx % cols_pad;
+  if (i >= cols) return;
+  float acc = 0.f;
+  for (int z = 0; z < nsplit; ++z) acc += part[(size_t)z * rows * cols_pad + idx];
+  out[(size_t)o * ld_out + i] = acc;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// NAIS-Net stability projection (Functions/naisnet.py:30-39), once per iteration instead of per net_u call:
+//   R = W^T W;  n = ||R||_F;  s = sqrt(delta)/sqrt(n) if n > delta else 1;  Bm = -(s R + eps I)
+// state[0] = n, state[1] = s, state[2] = 1 if scaled.     Single block.
+// ----------------------------------------------------------------------------------------------------
+__global__ void nais_project_kernel(const float* __restrict__ Rm, int H, float eps, float* __restrict__ Bm,
+                                    float* __restrict__ state) {
+  __shared__ double red[32];
+  __shared__ float sh_s;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) acc += (double)Rm[i] * (double)Rm[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float n = (float)sqrt(acc);
+    const float delta = 1.f - 2.f * eps;
+    const bool scaled = n > delta;
+    const float s = scaled ? sqrtf(delta) / sqrtf(n) : 1.f;
+    state[0] = n, state[1] = s, state[2] = scaled ? 1.f : 0.f;
+    sh_s = s;
+  }
+  __syncthreads();
+  const float s = sh_s;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+    const int r = i / H, c = i % H;
+    Bm[i] = -(s * Rm[i] + (r == c ? eps : 0.f));
+  }
+}
+// Backward of the projection: Sm = Rbar + Rbar^T with Rbar = s*(-Bbar) - [scaled] 0.5 s <-Bbar, R>/n^2 R;
+// the caller then forms Wbar = W * Sm with the GEMM.
+__global__ void nais_project_bwd_kernel(const float* __restrict__ Bbar, const float* __restrict__ Rm, int H,
+                                        const float* __restrict__ state, float* __restrict__ Sm) {
+  __shared__ double red[32];
+  __shared__ float sh_k;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) acc -= (double)Bbar[i] * (double)Rm[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float n = state[0], s = state[1];
+    sh_k = state[2] != 0.f ? (float)(0.5 * (double)s * acc / ((double)n * (double)n)) : 0.f;
+  }
+  __syncthreads();
+  const float s = state[1], k = sh_k;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+    const int r = i / H, c = i % H, it = c * H + r;
+    Sm[i] = (-s * Bbar[i] - k * Rm[i]) + (-s * Bbar[it] - k * Rm[it]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// clip_grad_norm_(max_norm) + Adam (torch.optim.Adam defaults; with_corr_high_dimension_pde.py:424-425)
+// opt_state (device, 64 B): [0] int64 step | [8] float clip_coef | [12] float step_size | [16] float bc2_sqrt
+//                            | [20] float grad_norm
+// ----------------------------------------------------------------------------------------------------
+struct OptState {
+  long long step;
+  float clip_coef, step_size, bc2_sqrt, grad_norm;
+};
+
+__global__ void gradsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fmaf(g[i], g[i], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+__global__ void opt_prepare_kernel(const float* __restrict__ part, int npart, FbsnnAdam hp, OptState* st) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < npart; i += blockDim.x) acc += (double)part[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float norm = (float)sqrt(acc);
+    float coef = 1.f;
+    if (hp.max_grad_norm > 0.0) coef = fminf((float)hp.max_grad_norm / (norm + 1e-6f), 1.f);
+    const long long step = st->step + 1;
+    const double bc1 = 1.0 - pow(hp.beta1, (double)step);
+    const double bc2 = 1.0 - pow(hp.beta2, (double)step);
+    st->step = step;
+    st->clip_coef = coef;
+    st->step_size = (float)(hp.lr / bc1);
+    st->bc2_sqrt = (float)sqrt(bc2);
+    st->grad_norm = norm;
+  }
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float beta1, float beta2, float eps,
+                            const OptState* __restrict__ st) {
+  const float coef = st->clip_coef, step_size = st->step_size, bc2s = st->bc2_sqrt;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);          // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2s + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+
+}  // namespace fbsnn

@@ -1,0 +1,146 @@
+/*
+ * fbsnn_b200.h -- C-ABI of the B200 (sm_100a) forward-backward-SDE training step and the correlated-GBM
+ * basket Monte-Carlo pricer.
+ *
+ * The reference (timothykski/Deep-neural-network-solutions-for-partial-differential-equations) has no FFI of
+ * its own: its boundary is the Python class surface.  Each entry point below states the
+ * reference method it replaces.  All pointers are DEVICE pointers unless the name says `host`; every call
+ * enqueues work on `stream` and returns without synchronising (no allocation, no host sync => graph-capturable).
+ * Return value: 0 on success, a negative FBSNN_E_* code otherwise; fbsnn_last_error() gives the message.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ */
+#ifndef FBSNN_B200_H
+#define FBSNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBSNN_MAX_HIDDEN 8
+
+enum { FBSNN_OK = 0, FBSNN_E_BADARG = -1, FBSNN_E_UNSUPPORTED = -2, FBSNN_E_CUDA = -3, FBSNN_E_WORKSPACE = -4 };
+
+/* network topology: reference `mode` strings "FC" (DeepBSDE.py:166-172) and "Naisnet"/"NAIS-Net"
+ * (Functions/naisnet.py:6-95) */
+enum { FBSNN_NET_FC = 0, FBSNN_NET_NAIS = 1 };
+/* activation: Functions/Sine.py:6-12, nn.ReLU, nn.Tanh (with_corr_high_dimension_pde.py:157-162) */
+enum { FBSNN_ACT_SINE = 0, FBSNN_ACT_RELU = 1, FBSNN_ACT_TANH = 2 };
+/* closed enumeration of the reference's mu_tf / sigma_tf / phi_tf / g_tf callables */
+enum { FBSNN_MU_ZERO = 0, FBSNN_MU_LINEAR = 1 };            /* 0 | mu_c * X                                   */
+enum { FBSNN_SIGMA_CONST = 0, FBSNN_SIGMA_PROP = 1 };       /* sigma_c * I | sigma_c * diag(X)                */
+enum { FBSNN_PHI_BSB = 0, FBSNN_PHI_RY = 1, FBSNN_PHI_ZSQ = 2 }; /* c(Y - X.Z) | c Y | |Z|^2                   */
+enum { FBSNN_G_SUMSQ = 0, FBSNN_G_CALL_SUM = 1, FBSNN_G_CALL_MEAN = 2, FBSNN_G_LOGQ = 3 };
+/* arithmetic variant of the dense layers */
+enum { FBSNN_PREC_FP32 = 0,      /* SIMT fp32 FMA: parity-grade (tolerances in tests/test_parity_gpu.py)     */
+       FBSNN_PREC_TF32 = 1 };    /* tcgen05 kind::tf32, fp32 accumulate in TMEM: large-M throughput variant  */
+
+typedef struct FbsnnSpec {
+  int32_t D;                          /* state dimension                                                      */
+  int32_t N;                          /* Euler-Maruyama steps; rows per path = N + 1                          */
+  int32_t n_hidden;                   /* hidden layers L (FC: len(layers)-2; NAIS: stable blocks + 1)         */
+  int32_t width[FBSNN_MAX_HIDDEN];    /* hidden widths, each a multiple of 4; NAIS: all equal                 */
+  int32_t net_kind, act_kind;
+  int32_t mu_kind, sigma_kind, phi_kind, g_kind;
+  float mu_c, sigma_c, phi_c, strike;
+  float nais_eps;                     /* 0.01 in the reference (Functions/naisnet.py:27)                      */
+  int32_t precision;
+  /* offsets (in floats, multiples of 4) into the flat parameter / gradient / Adam buffers; index l = 1..L is
+   * hidden layer l, index L+1 the scalar output layer; -1 = absent.  Matrices are PyTorch (out, in) row-major. */
+  int64_t off_W[FBSNN_MAX_HIDDEN + 2];    /* FC: Linear l weight; NAIS: layer{l}.weight                       */
+  int64_t off_b[FBSNN_MAX_HIDDEN + 2];
+  int64_t off_Win[FBSNN_MAX_HIDDEN + 2];  /* NAIS layer{l}_input.weight (l = 2..L)                            */
+  int64_t off_bin[FBSNN_MAX_HIDDEN + 2];
+  int64_t n_params;                       /* length of the flat buffers in floats (incl. alignment padding)   */
+} FbsnnSpec;
+
+/* Adam + clip_grad_norm_ hyper-parameters (torch.optim.Adam defaults, DeepBSDE.py:272;
+ * clip: with_corr_high_dimension_pde.py:424).  max_grad_norm <= 0 disables clipping. */
+typedef struct FbsnnAdam {
+  double lr, beta1, beta2, eps, max_grad_norm;
+} FbsnnAdam;
+
+const char* fbsnn_last_error(void);
+int fbsnn_version(void);
+/* Measurement hooks used by bench.py: number of kernels this library has launched since it was loaded; and
+ * optional CUDA-event timing of every dense-layer launch (enable, run, synchronise, read).
+ * out6 = {launches, ms, algorithmic FLOPs, tcgen05 launches, tcgen05 ms, tcgen05 FLOPs}. */
+long long fbsnn_launch_count(void);
+void fbsnn_dense_timing(int enable);
+int fbsnn_dense_timing_read(double* out6);
+
+/* Bytes of device scratch needed for `n_paths` paths (rows = n_paths * (N+1)).  `with_grad` = 0 sizes for
+ * forward/predict only. */
+int fbsnn_workspace_bytes(const FbsnnSpec* spec, int64_t n_paths, int with_grad, size_t* bytes_out);
+
+/* Replaces FBSNN.fetch_minibatch (DeepBSDE.py:247-262; correlated: with_corr_high_dimension_pde.py:316-353)
+ * on the device: t (M,N+1,1) and cumulative W (M,N+1,D), Philox4x32-10 keyed (seed, iteration, global path id).
+ * `chol` = lower Cholesky factor (D,D) row-major or NULL.  Not stream-compatible with NumPy's MT19937. */
+int fbsnn_fetch_minibatch(const FbsnnSpec* spec, float T, int64_t n_paths, int64_t path_offset, uint64_t seed,
+                          uint64_t iteration, const float* chol, void* workspace, size_t workspace_bytes,
+                          float* t_out, float* W_out, void* stream);
+
+/* Replaces FBSNN.net_u (DeepBSDE.py:189-194): u (rows,) and Du (rows, D) for arbitrary (t, X) rows. */
+int fbsnn_net_u(const FbsnnSpec* spec, const float* params, const float* t, const float* X, int64_t rows,
+                void* workspace, size_t workspace_bytes, float* u_out, float* du_out, void* stream);
+
+/* Replaces FBSNN.loss_function forward / FBSNN.predict (DeepBSDE.py:202-245, 297-302).
+ * t (M,N+1,1), W (M,N+1,D) cumulative as the reference passes them; Xi (xi_rows, D), xi_rows in {1, M}.
+ * Outputs (any may be NULL): X (M,N+1,D), Y (M,N+1), Z (M,N+1,D), loss (1). */
+int fbsnn_forward(const FbsnnSpec* spec, const float* params, const float* t, const float* W, const float* Xi,
+                  int64_t xi_rows, int64_t n_paths, void* workspace, size_t workspace_bytes, float* X_out,
+                  float* Y_out, float* Z_out, float* loss_out, void* stream);
+
+/* loss_function + loss.backward() (DeepBSDE.py:278-279): as fbsnn_forward, plus the gradient of the summed
+ * loss w.r.t. every parameter written (not accumulated) into `grads` (flat, same layout as params).
+ * If W == NULL the Brownian increments are drawn in-kernel (Philox, as fbsnn_fetch_minibatch with the same
+ * seed/iteration/path_offset, t_n = n T/N) and `t` is ignored. */
+int fbsnn_loss_grad(const FbsnnSpec* spec, const float* params, float* grads, const float* t, const float* W,
+                    const float* Xi, int64_t xi_rows, int64_t n_paths, float T, int64_t path_offset,
+                    uint64_t seed, uint64_t iteration, const float* chol, void* workspace,
+                    size_t workspace_bytes, float* X_out, float* Y_out, float* Z_out, float* loss_out,
+                    void* stream);
+
+/* clip_grad_norm_ + Adam.step on the flat buffers (with_corr_high_dimension_pde.py:424-425).  `opt_state` is
+ * FBSNN_OPT_STATE_BYTES of device memory: int64 step counter at byte 0 (zero-initialised by the caller when the
+ * optimizer is created -- the reference builds a fresh Adam per train() call, DeepBSDE.py:272), then float
+ * clip_coef @8, step_size @12, sqrt(bias_correction2) @16, grad_norm @20, and reduction scratch from byte 64.
+ * The step counter is advanced on the device, so the call can be replayed from a CUDA graph. */
+#define FBSNN_OPT_STATE_BYTES 2048
+int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads, float* exp_avg,
+                    float* exp_avg_sq, int64_t n_params, void* opt_state, void* stream);
+
+/* One fused training iteration on one GPU = fbsnn_loss_grad + fbsnn_adam_step.  Multi-GPU callers run
+ * fbsnn_loss_grad, all-reduce [grads | loss] over NCCL, then fbsnn_adam_step. */
+int fbsnn_train_step(const FbsnnSpec* spec, const FbsnnAdam* host_hp, float* params, float* grads,
+                     float* exp_avg, float* exp_avg_sq, void* opt_state, const float* t, const float* W,
+                     const float* Xi, int64_t xi_rows, int64_t n_paths, float T, int64_t path_offset,
+                     uint64_t seed, uint64_t iteration, const float* chol, void* workspace,
+                     size_t workspace_bytes, float* X_out, float* Y_out, float* loss_out, void* stream);
+
+/* ---- Monte-Carlo basket pricer (numerics/multidimensional_mc_pricer.py) --------------------------------- */
+typedef struct McSpec {
+  int32_t D, N;          /* assets, time steps                                                                */
+  float rate, sigma, T, strike;
+} McSpec;
+
+/* Replaces MonteCarloPricer.price = generate_paths + payoff + discounted mean (:49-93) without storing paths.
+ * Simulates global paths [path_offset, path_offset + n_paths); writes sums_out[0] = sum of discounted payoffs,
+ * sums_out[1] = sum of squares (double).  chol_T = TRANSPOSED lower Cholesky factor (chol_T[j*D+d] = L[d][j])
+ * or NULL for independent assets.  scratch: mc_scratch_bytes(). */
+size_t mc_scratch_bytes(void);
+long long mc_launch_count(void);   /* kernels launched by the pricer since load (bench.py's gpu_launches) */
+int mc_basket_price(const McSpec* spec, const float* S0, const float* weights, const float* chol_T,
+                    uint64_t n_paths, uint64_t seed, uint64_t path_offset, void* scratch, double* sums_out,
+                    void* stream);
+
+/* Replaces BlackScholesModel.generate_paths (:49-67): paths_out (n_paths, N+1, D) float32. */
+int mc_generate_paths(const McSpec* spec, const float* S0, const float* chol_T, uint64_t n_paths,
+                      uint64_t seed, uint64_t path_offset, float* paths_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBSNN_B200_H */

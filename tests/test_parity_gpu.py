@@ -1,0 +1,92 @@
+"""GPU parity: the CUDA path (through the C-ABI, via the reference-shaped Python classes) against the outputs
+of the unmodified reference stored in tests/golden (same initial weights, same NumPy Brownian stream).
+
+Tolerances (fp32 SIMT variant), relative unless noted -- the reference's own fp32-vs-fp64 gap is ~1e-7 on the
+loss; the bars below allow for a different (but still fp32) summation order in the dense layers:
+    loss 2e-5 | Y 2e-5 of max|Y| | X 1e-5 abs | Z rel-L2 1e-4 | per-tensor gradient 1e-3 of its max |
+    after K Adam iterations: loss 5e-3, Y0 5e-3 abs, last-layer weights 2e-2 of max
+(Adam's first steps are sign-like, so round-off in near-zero gradient entries moves single weights by ~lr.)
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(loss_rel=2e-5, Y_rel=2e-5, X_abs=1e-5, Z_rel_l2=1e-4, grad_rel_max=1e-3, gradnorm_rel=2e-4,
+           trace_loss_rel=5e-3, trace_Y0_abs=5e-3, final_w_rel=2e-2)
+
+
+@pytest.mark.parametrize("name", gu.solver_cases())
+def test_cuda_matches_reference(name):
+    from tests import parity_util as pu
+    g, meta = gu.load(name)
+    sol, oracle = pu.build_cuda_solver(meta, g)
+    errs = pu.single_eval_errors(sol, oracle, g, meta)
+    for k, v in errs.items():
+        if k in TOL:
+            assert v <= TOL[k], (name, k, v, errs)
+    if meta["D"] == 1 and meta["M"] > 1:
+        return  # the reference trace of this case contains the cross-path broadcast
+    terr = pu.train_trace_errors(sol, g, meta)
+    for k, v in terr.items():
+        assert v <= TOL[k], (name, k, v, terr)
+
+
+def test_train_api_matches_reference_graph():
+    """DeepBSDE.FBSNN.train() end to end: returned graph, then predict() on the np.random.seed(42) batch."""
+    import dnnpde_b200 as pde
+    g, meta = gu.load("bsb100_train_api")
+    g0, meta0 = gu.load("bsb100_fc_sine")
+    oracle = gu.rebuild_inputs(meta0, g0)
+    np.random.seed(meta["numpy_seed"])
+    D, M, N = meta["D"], meta["M"], meta["N"]
+    sol = pde.BlackScholesBarenblatt(gu.make_xi("bsb", D), 1.0, M, N, D, [D + 1] + 4 * [256] + [1], "FC", "Sine")
+    sol.model.load_state_dict(oracle.model.state_dict())
+    graph = sol.train(3, 1e-3)
+    assert graph.shape == (2, 1) and graph[0, 0] == 0
+    assert abs(graph[1, 0] - g["graph"][1, 0]) <= 2e-5 * g["graph"][1, 0]
+    np.random.seed(42)
+    t_test, W_test = sol.fetch_minibatch()
+    X_pred, Y_pred = sol.predict(gu.make_xi("bsb", D), t_test, W_test)
+    assert X_pred.shape == (M, N + 1, D) and Y_pred.shape == (M, N + 1, 1)
+    ref = g["Y_pred"]
+    assert np.abs(Y_pred[:, :, 0].cpu().numpy() - ref).max() <= 5e-3 * np.abs(ref).max()
+    assert np.abs(X_pred[:2].cpu().numpy() - g["X_pred_head"]).max() <= 1e-5
+
+
+def test_loss_backward_surface():
+    """loss_function(...)[0].backward() fills p.grad; net_u agrees with the trajectories of loss_function."""
+    import dnnpde_b200 as pde
+    torch.manual_seed(3)
+    np.random.seed(3)
+    D, M, N = 10, 17, 7
+    sol = pde.BSPDETestCase(np.ones((1, D)), 1.0, M, N, D, None, [D + 1, 32, 32, 1], "FC", "Tanh")
+    t, W = sol.fetch_minibatch()
+    loss, X, Y, Y0 = sol.loss_function(t, W, sol.Xi)
+    sol.model.zero_grad()
+    loss.backward()
+    _, _, _, _, flat = sol.loss_grad_flat(t, W)
+    for n, p in sol.model.named_parameters():
+        o = sol._fp.offsets[n]
+        assert torch.equal(p.grad.reshape(-1), flat[o:o + p.numel()])
+    u, du = sol.net_u(t[:, 3, :], X[:, 3, :])
+    assert torch.allclose(u, Y[:, 3, :], rtol=1e-5, atol=1e-6)
+    assert u.shape == (M, 1) and du.shape == (M, D)
+
+
+def test_unknown_problem_raises():
+    import dnnpde_b200 as pde
+
+    class Custom(pde.FBSNN):
+        def phi_tf(self, t, X, Y, Z): return Y
+        def g_tf(self, X): return X.sum(1, keepdim=True)
+        def mu_tf(self, t, X, Y, Z): return X
+        def sigma_tf(self, t, X, Y): return torch.diag_embed(X)
+
+    sol = Custom(np.ones((1, 4)), 1.0, 8, 4, 4, [5, 16, 16, 1], "FC", "Sine")
+    t, W = sol.fetch_minibatch()
+    with pytest.raises(NotImplementedError):
+        sol.loss_function(t, W, sol.Xi)

@@ -153,112 +153,127 @@ def workload_config(args):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Ctx:
+    pass
+
+
+def setup(args):
     import torch.distributed as dist
 
     import dnnpde_b200 as pde
     from dnnpde_b200 import parallel
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
+    c = Ctx()
+    c.pde, c.parallel, c.dist = pde, parallel, dist
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(c.local)
+    c.dev = torch.device("cuda", c.local)
+    if c.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = pde._lib.load()
-    pk = peaks()
+        dist.init_process_group("nccl", device_id=c.dev)
+    c.lib = pde._lib.load()
 
     def barrier():
-        if world > 1:
+        if c.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world > 1:
-            tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if c.world > 1:
+            tt = torch.tensor([x], dtype=torch.float64, device=c.dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt)
         return x
 
+    c.barrier, c.max_over_ranks = barrier, max_over_ranks
+    return c
+
+
+def make_solver(c, args):
+    """Solver + `nbatch` resident synthetic minibatches (reference layout), generated on the device by Philox."""
+    import ctypes
+    pde = c.pde
     M = args.paths
     torch.manual_seed(1234)
     sol = pde.BlackScholesBarenblatt(xi_bsb(), 1.0, M, NSTEPS, D, LAYERS, "FC", "Sine", precision=args.precision,
                                      data_parallel=True)
-    lo, hi = parallel.shard_range(M, rank, world)
+    lo, hi = c.parallel.shard_range(M, c.rank, c.world)
     m_loc = hi - lo
-
-    # resident synthetic minibatches (reference layout, cumulative t and W), generated on the device
-    import ctypes
     sp = sol._spec()
-    ws = sol._workspace(lib, sp, m_loc, True)
-    nbatch = 2
+    ws = sol._workspace(c.lib, sp, m_loc, True)
     batches = []
-    for b in range(nbatch):
-        t = torch.empty(m_loc, NSTEPS + 1, 1, device=dev)
-        W = torch.empty(m_loc, NSTEPS + 1, D, device=dev)
-        rc = lib.fbsnn_fetch_minibatch(ctypes.byref(sp), 1.0, m_loc, lo, 777, b, None, ctypes.c_void_p(ws.data_ptr()),
-                                       ws.numel(), ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(W.data_ptr()),
-                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    for b in range(2):
+        t = torch.empty(m_loc, NSTEPS + 1, 1, device=c.dev)
+        W = torch.empty(m_loc, NSTEPS + 1, D, device=c.dev)
+        rc = c.lib.fbsnn_fetch_minibatch(ctypes.byref(sp), 1.0, m_loc, lo, 777, b, None, ctypes.c_void_p(ws.data_ptr()),
+                                         ws.numel(), ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(W.data_ptr()),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         pde._lib.check(rc, "fbsnn_fetch_minibatch")
         batches.append((t, W))
-    loss_buf = torch.zeros(args.warmup + args.steps + 8, device=dev)
+    return sol, batches, m_loc
 
-    # ---- value: K steps, inputs resident in HBM, CUDA events, max over ranks --------------------------------
+
+def measure_value(c, args, sol, batches):
+    """K training iterations, minibatches resident in HBM, CUDA events on the launching stream, max over ranks."""
+    nb = len(batches)
+    loss_buf = torch.zeros(args.warmup + args.steps + 1, device=c.dev)
     sol.begin_training(1e-3)
     for i in range(args.warmup):
-        t, W = batches[i % nbatch]
-        sol.training_step(t, W, loss_buf[i:i + 1])
-    barrier()
-    clocks = ClockSampler(local)
+        sol.training_step(*batches[i % nb], loss_buf[i:i + 1])
+    c.barrier()
+    clocks = ClockSampler(c.local)
     clocks.start()
-    l0 = lib.fbsnn_launch_count()
+    l0 = c.lib.fbsnn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        t, W = batches[i % nbatch]
-        sol.training_step(t, W, loss_buf[args.warmup + i:args.warmup + i + 1])
+        sol.training_step(*batches[i % nb], loss_buf[args.warmup + i:args.warmup + i + 1])
     e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = (lib.fbsnn_launch_count() - l0) // args.steps
+    c.barrier()
+    ms = c.max_over_ranks(e0.elapsed_time(e1))
+    launches = (c.lib.fbsnn_launch_count() - l0) // args.steps
     clk = clocks.stop()
-    ms_per_step = ms / args.steps
-    value = 1e3 / ms_per_step
-    final_loss = float(loss_buf[args.warmup + args.steps - 1])
+    return ms / args.steps, int(launches), clk, float(loss_buf[args.warmup + args.steps - 1])
 
-    # ---- roofline of the dominant kernel (dense-layer GEMM): per-launch CUDA events, live ---------------------
-    lib.fbsnn_dense_timing(1)
-    t, W = batches[0]
-    sol.training_step(t, W, loss_buf[-1:])
+
+def measure_roofline(c, args, sol, batches, ms_per_step, m_loc):
+    """Dominant kernel = the dense-layer GEMM: per-launch CUDA events around every dense launch of one more step."""
+    import ctypes
+    pk = peaks()
+    loss = torch.zeros(1, device=c.dev)
+    c.lib.fbsnn_dense_timing(1)
+    sol.training_step(*batches[0], loss)
     torch.cuda.synchronize()
     out6 = (ctypes.c_double * 6)()
-    pde._lib.check(lib.fbsnn_dense_timing_read(out6), "timing")
-    lib.fbsnn_dense_timing(0)
+    c.pde._lib.check(c.lib.fbsnn_dense_timing_read(out6), "timing")
+    c.lib.fbsnn_dense_timing(0)
     n_dense, dense_ms, dense_flops = int(out6[0]), out6[1], out6[2]
     achieved = dense_flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
     tc_peak = pk["bf16"] * 0.5          # kind::tf32 issues at half the bf16 rate (nominal 1.1 vs 2.25 PFLOP/s)
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                "frac": achieved / tc_peak, "traffic": None,
-                "kernel": "gemm_tc_kernel (tcgen05 kind::tf32)" if out6[3] > 0 else "gemm_simt_kernel (fp32 FMA)",
-                "launches_per_step": n_dense, "dense_ms_per_step": dense_ms,
-                "dense_share_of_step": dense_ms / ms_per_step,
-                "peak_source": f"{pk['source']} bf16 {pk['bf16']} TFLOP/s x 0.5 (tf32 rate)",
-                "step_tflops": FLOP_PER_ROW * m_loc * (NSTEPS + 1) / (ms_per_step * 1e-3) / 1e12}
+    return {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+            "traffic": None,
+            "kernel": "gemm_tc_kernel (tcgen05 kind::tf32)" if out6[3] > 0 else "gemm_simt_kernel (fp32 FMA)",
+            "launches_per_step": n_dense, "dense_ms_per_step": dense_ms, "dense_share_of_step": dense_ms / ms_per_step,
+            "tc_launches": int(out6[3]), "tc_ms": out6[4],
+            "tc_tflops": (out6[5] / (out6[4] * 1e-3) / 1e12) if out6[4] > 0 else None,
+            "peak_source": f"{pk['source']} bf16 {pk['bf16']} TFLOP/s x 0.5 (tf32 rate)",
+            "step_tflops": FLOP_PER_ROW * m_loc * (NSTEPS + 1) / (ms_per_step * 1e-3) / 1e12}
 
-    # ---- e2e: the public train() API, minibatch copied from pinned host memory every step ---------------------
-    host = []
-    for b in range(nbatch):
-        host.append((batches[b][0].cpu().pin_memory(), batches[b][1].cpu().pin_memory()))
+
+def measure_e2e(c, args, sol, batches):
+    """The public train() API with the minibatch copied from pinned host memory every step (double-buffered on a
+    copy stream, every byte crosses PCIe inside the timed region) and the per-step losses read back at the end."""
+    import contextlib
+    import io
+    dev = c.dev
+    host = [(t.cpu().pin_memory(), W.cpu().pin_memory()) for t, W in batches]
     copy_stream = torch.cuda.Stream(device=dev)
-
-    # fetch_minibatch() override: hands out the batch whose H2D copy was issued on the copy stream one call
-    # earlier and issues the next copy (double buffered); every byte crosses PCIe inside the timed region.
     state = {"i": 0, "pending": None}
 
     def issue(i):
-        th, Wh = host[i % nbatch]
+        th, Wh = host[i % len(host)]
         with torch.cuda.stream(copy_stream):
             td = torch.empty(th.shape, device=dev)
             Wd = torch.empty(Wh.shape, device=dev)
@@ -272,78 +287,86 @@ def run_ours(args):
         if state["pending"] is None:
             state["pending"] = issue(state["i"])
         td, Wd, ev = state["pending"]
-        torch.cuda.current_stream().wait_event(ev)
-        td.record_stream(torch.cuda.current_stream()), Wd.record_stream(torch.cuda.current_stream())
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        td.record_stream(cur), Wd.record_stream(cur)
         state["i"] += 1
         state["pending"] = issue(state["i"])
         return td, Wd
 
     sol.fetch_minibatch = fetch
-    sol.M = M
-    import contextlib
-    import io
     with contextlib.redirect_stdout(io.StringIO()):
         sol.train(max(1, args.warmup), 1e-3)
-        barrier()
+        c.barrier()
         t0 = time.perf_counter()
         sol.train(args.steps, 1e-3)
-        barrier()
-        e2e_sec = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = args.steps / e2e_sec
+        c.barrier()
+        sec = c.max_over_ranks(time.perf_counter() - t0)
     h2d = int((host[0][0].numel() + host[0][1].numel()) * 4)
-    e2e = {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-           "api": "BlackScholesBarenblatt.train(K, lr) with host-supplied Brownian minibatches (pinned, "
-                  "double-buffered H2D on a copy stream)"}
+    return {"value": args.steps / sec, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+            "api": "BlackScholesBarenblatt.train(K, lr), host-supplied Brownian minibatches (pinned, double-buffered "
+                   "H2D on a copy stream), losses and Y0 read back"}
 
+
+def measure_mc(c, args):
+    pde = c.pde
+    np.random.seed(0)
+    model = pde.BlackScholesModel(0.05, 0.2, D, True)
+    pr = pde.MonteCarloPricer(model, pde.BasketOption(np.ones(D) / D, 1.0), 1.0, NSTEPS, args.mc_paths, seed=7,
+                              data_parallel=True)
+    n_lo, n_hi = c.parallel.shard_range(args.mc_paths, c.rank, c.world)
+    pr.price_async(np.ones(D), max(1, (n_hi - n_lo) // 16), n_lo, 7)      # warm-up
+    c.barrier()
+    m0 = c.lib.mc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sums = pr.price_async(np.ones(D), n_hi - n_lo, n_lo, 7)
+    e1.record()
+    c.barrier()
+    mc_ms = c.max_over_ranks(e0.elapsed_time(e1))
+    c.parallel.allreduce_sums(sums)
+    s, q = (float(v) for v in sums.cpu())
+    mean = s / args.mc_paths
+    se = float(np.sqrt(max(q / args.mc_paths - mean * mean, 0.0) / args.mc_paths))
+    pps = args.mc_paths / (mc_ms * 1e-3)
+    return {"metric": "MC basket paths/s", "value": pps, "unit": "paths/s", "paths": args.mc_paths, "ms": mc_ms,
+            "price": mean, "stderr": se, "normals_per_s": pps * NSTEPS * D,
+            "gpu_launches": int(c.lib.mc_launch_count() - m0),
+            "form": "N*D Philox/Box-Muller normals per path, Cholesky matvec hoisted (L sum_t z_t)"}
+
+
+def run_ours(args):
+    c = setup(args)
+    sol, batches, m_loc = make_solver(c, args)
+    ms_per_step, launches, clk, final_loss = measure_value(c, args, sol, batches)
     line = {
-        "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "iters/s", "n_gpus": c.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-        "config": workload_config(args), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "final_loss": final_loss,
+        "config": workload_config(args), "clocks": clk, "gpu_launches": launches, "final_loss": final_loss,
     }
-
-    # ---- secondary metric: Monte-Carlo basket paths/s (D=100, N=50, correlated) -------------------------------
+    line["roofline"] = measure_roofline(c, args, sol, batches, ms_per_step, m_loc)
+    if not args.skip_e2e:
+        line["e2e"] = measure_e2e(c, args, sol, batches)
+    del sol, batches
+    torch.cuda.empty_cache()
     if not args.skip_mc:
-        np.random.seed(0)
-        model = pde.BlackScholesModel(0.05, 0.2, D, True)
-        pr = pde.MonteCarloPricer(model, pde.BasketOption(np.ones(D) / D, 1.0), 1.0, NSTEPS, args.mc_paths, seed=7,
-                                  data_parallel=True)
-        n_lo, n_hi = parallel.shard_range(args.mc_paths, rank, world)
-        pr.price_async(np.ones(D), max(1, (n_hi - n_lo) // 16), n_lo, 7)      # warm-up
-        barrier()
-        m0 = lib.mc_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        sums = pr.price_async(np.ones(D), n_hi - n_lo, n_lo, 7)
-        e1.record()
-        barrier()
-        mc_ms = max_over_ranks(e0.elapsed_time(e1))
-        parallel.allreduce_sums(sums)
-        s, q = (float(v) for v in sums.cpu())
-        mean = s / args.mc_paths
-        se = float(np.sqrt(max(q / args.mc_paths - mean * mean, 0.0) / args.mc_paths))
-        pps = args.mc_paths / (mc_ms * 1e-3)
-        line["mc"] = {"metric": "MC basket paths/s", "value": pps, "unit": "paths/s", "paths": args.mc_paths,
-                      "ms": mc_ms, "price": mean, "stderr": se, "normals_per_s": pps * NSTEPS * D,
-                      "gpu_launches": int(lib.mc_launch_count() - m0),
-                      "form": "N*D Philox/Box-Muller normals per path, Cholesky matvec hoisted (L sum_t z_t)"}
-
-    # ---- CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample ----------------------
-    if rank == 0 and world == 1 and not args.skip_cpu:
+        line["mc"] = measure_mc(c, args)
+    # CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample
+    if c.rank == 0 and c.world == 1 and not args.skip_cpu:
         cores = os.cpu_count()
         torch.set_num_threads(cores)
-        v, sec = cpu_train_rate(M, args.cpu_sample_paths, 3, 1)
+        v, sec = cpu_train_rate(args.paths, args.cpu_sample_paths, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "iters/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_sample_paths} of {M} paths per step ({sec:.2f} s/step), "
+                                "sample": f"{args.cpu_sample_paths} of {args.paths} paths per step ({sec:.2f} s/step), "
                                           "scaled linearly in paths"}
         if not args.skip_mc:
             line["mc"]["cpu_baseline"] = {"value": cpu_mc_rate(20000), "unit": "paths/s", "cores": 1, "kind": "port",
                                           "sample": "20000 paths, D=100, N=50"}
-    if rank == 0:
+    if c.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if c.world > 1:
+        c.dist.destroy_process_group()
 
 
 def main():
@@ -358,6 +381,7 @@ def main():
     ap.add_argument("--cpu-sample-paths", type=int, default=256)
     ap.add_argument("--skip-mc", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (the JSON line then has no e2e)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libfbsnn_b200.so (and there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES + ["-lcuda"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
@@ -64,6 +64,8 @@ def _declare(lib):
     lib.fbsnn_dense_timing.argtypes = [c.c_int]
     lib.fbsnn_dense_timing_read.restype = c.c_int
     lib.fbsnn_dense_timing_read.argtypes = [c.POINTER(c.c_double)]
+    lib.fbsnn_debug_gemm.restype = c.c_int
+    lib.fbsnn_debug_gemm.argtypes = [c.c_int] * 6 + [f32p, c.c_int, f32p, c.c_int, f32p, c.c_int, vp]
     lib.fbsnn_workspace_bytes.restype = c.c_int
     lib.fbsnn_workspace_bytes.argtypes = [c.POINTER(S.FbsnnSpec), i64, c.c_int, c.POINTER(sz)]
     lib.fbsnn_fetch_minibatch.restype = c.c_int
@@ -94,7 +96,7 @@ def _declare(lib):
 
 
 EXPORTS = ["fbsnn_last_error", "fbsnn_version", "fbsnn_launch_count", "fbsnn_dense_timing",
-           "fbsnn_dense_timing_read", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
+           "fbsnn_dense_timing_read", "fbsnn_debug_gemm", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
            "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_adam_step", "fbsnn_train_step", "mc_scratch_bytes", "mc_launch_count",
            "mc_basket_price", "mc_generate_paths"]
 

@@ -50,6 +50,9 @@ constexpr int kMaxL = FBSNN_MAX_HIDDEN;
 
 struct Plan {
   int D, N, L, ldx, ldi, d_in;
+  bool tf32;
+  int kin, ldw;   // K extent / leading dimension of the input-width weight operands (padded to ldx in TF32 mode)
+  size_t W1p, Winp[kMaxL + 2];
   int H[kMaxL + 2];
   bool nais;
   long long rows;
@@ -90,7 +93,11 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   memset(&p, 0, sizeof(p));
   p.D = s->D, p.N = s->N, p.L = s->n_hidden;
   p.d_in = s->D + 1;
-  p.ldx = round_up(p.d_in, 4);
+  p.tf32 = s->precision == FBSNN_PREC_TF32;
+  // TF32 variant: the input width is zero-padded to a multiple of 32 so that every dense layer is a TMA/UMMA tile
+  p.ldx = round_up(p.d_in, p.tf32 ? 32 : 4);
+  p.kin = p.tf32 ? p.ldx : p.d_in;
+  p.ldw = p.kin;
   p.ldi = round_up(s->D, 4);
   p.nais = s->net_kind == FBSNN_NET_NAIS;
   p.rows = rows;
@@ -129,6 +136,11 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
       const size_t hh = (size_t)p.H[l] * p.H[l];
       p.Bm[l] = take(hh), p.Rm[l] = take(hh), p.nstate[l] = take(4);
     }
+  if (p.tf32) {
+    p.W1p = take((size_t)p.H[1] * p.ldx);
+    if (p.nais)
+      for (int l = 2; l <= p.L; ++l) p.Winp[l] = take((size_t)p.H[l] * p.ldx);
+  }
   if (with_grad) {
     p.V = take(R * p.ldx);
     p.ybar = take(R);
@@ -173,8 +185,9 @@ static bool g_timed_tc[kMaxTimed];
 
 // dense layer dispatch: SIMT fp32, or tcgen05 TF32 when the variant is selected and the shape qualifies
 template <bool A_KC, bool B_KC, class Epi>
-static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nsplit, cudaStream_t st, const char* what) {
-  const bool tc = s->precision == FBSNN_PREC_TF32 && tc_eligible<A_KC, B_KC>(g, nsplit);
+static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nsplit, cudaStream_t st, const char* what,
+                 bool allow_tc = true) {
+  const bool tc = allow_tc && s->precision == FBSNN_PREC_TF32 && tc_eligible<A_KC, B_KC>(g, nsplit);
   int slot = -1;
   if (g_timing && g_ntimed < kMaxTimed) {
     slot = g_ntimed++;
@@ -186,7 +199,7 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
     cudaEventRecord(g_ev0[slot], st);
   }
   ++g_launches;
-  cudaError_t e = tc ? launch_gemm_tc<A_KC, B_KC>(g, epi, num_sms(), st) : launch_gemm<A_KC, B_KC>(g, epi, nsplit, num_sms(), st);
+  cudaError_t e = tc ? launch_gemm_tc<A_KC, B_KC>(g, epi, nsplit, num_sms(), st) : launch_gemm<A_KC, B_KC>(g, epi, nsplit, num_sms(), st);
   if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
   if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "%s gemm %s: %s", tc ? "tcgen05" : "simt", what, cudaGetErrorString(e));
   return 0;
@@ -218,7 +231,26 @@ static Net bind_net(const FbsnnSpec* s, const Plan& p, const float* params, floa
   }
   n.wout = params + s->off_W[p.L + 1];
   n.bout = params + s->off_b[p.L + 1];
+  if (p.tf32) {   // zero-padded copies (H x ldx), refreshed by prepare_weights() every call
+    n.W[1] = ws + p.W1p;
+    if (p.nais)
+      for (int l = 2; l <= p.L; ++l) n.Win[l] = ws + p.Winp[l];
+  }
   return n;
+}
+
+// TF32 variant: copy the input-width matrices into their zero-padded (H x ldx) homes
+static int prepare_weights(const FbsnnSpec* s, const Plan& p, const float* params, float* ws, cudaStream_t st) {
+  if (!p.tf32) return 0;
+  for (int l = 1; l <= p.L; ++l) {
+    if (l >= 2 && !p.nais) break;
+    const float* src = params + (l == 1 ? s->off_W[1] : s->off_Win[l]);
+    float* dst = ws + (l == 1 ? p.W1p : p.Winp[l]);
+    const int n = p.H[l] * p.ldx;
+    pad_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, p.H[l], p.d_in, dst, p.ldx);
+    LAUNCH_CHECK("pad_copy");
+  }
+  return 0;
 }
 
 // NAIS projection, once per call: Bm_l = -(s W_l^T W_l + eps I)
@@ -228,7 +260,7 @@ static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* 
     GemmArgs g{};
     g.nseg = 1, g.M = H, g.N = H, g.Nb = H, g.kchunk = 0;
     g.seg[0] = GemmSeg{n.Wraw[l], n.Wraw[l], H, H, H};
-    int rc = dense<false, false>(s, g, EpiStore{ws + p.Rm[l], H}, 1, st, "nais RtR");
+    int rc = dense<false, false>(s, g, EpiStore{ws + p.Rm[l], H}, 1, st, "nais RtR", false);
     if (rc) return rc;
     nais_project_kernel<<<1, 1024, 0, st>>>(ws + p.Rm[l], H, s->nais_eps, ws + p.Bm[l], ws + p.nstate[l]);
     LAUNCH_CHECK("nais_project");
@@ -245,13 +277,13 @@ static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     g.M = R, g.N = p.H[l], g.Nb = p.H[l], g.kchunk = 0;
     if (l == 1) {
       g.nseg = 1;
-      g.seg[0] = GemmSeg{ws + p.xin, n.W[1], p.ldx, p.d_in, p.d_in};
+      g.seg[0] = GemmSeg{ws + p.xin, n.W[1], p.ldx, p.ldw, p.kin};
     } else {
       g.nseg = 1;
       g.seg[0] = GemmSeg{ws + p.h[l - 1], n.W[l], p.H[l - 1], p.H[l - 1], p.H[l - 1]};
       if (p.nais) {
         g.nseg = 2;
-        g.seg[1] = GemmSeg{ws + p.xin, n.Win[l], p.ldx, p.d_in, p.d_in};
+        g.seg[1] = GemmSeg{ws + p.xin, n.Win[l], p.ldx, p.ldw, p.kin};
       }
     }
     EpiFwd e{};
@@ -290,11 +322,11 @@ static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float
   }
   {
     GemmArgs g{};
-    g.M = R, g.N = p.ldx, g.Nb = p.d_in, g.kchunk = 0;
+    g.M = R, g.N = p.ldx, g.Nb = p.kin, g.kchunk = 0;
     g.nseg = 1;
-    g.seg[0] = GemmSeg{ws + p.delta[1], n.W[1], p.H[1], p.d_in, p.H[1]};
+    g.seg[0] = GemmSeg{ws + p.delta[1], n.W[1], p.H[1], p.ldw, p.H[1]};
     if (p.nais)
-      for (int l = 2; l <= p.L; ++l) g.seg[g.nseg++] = GemmSeg{ws + p.delta[l], n.Win[l], p.H[l], p.d_in, p.H[l]};
+      for (int l = 2; l <= p.L; ++l) g.seg[g.nseg++] = GemmSeg{ws + p.delta[l], n.Win[l], p.H[l], p.ldw, p.H[l]};
     int rc = dense<true, false>(s, g, EpiStore{ws + p.zf, p.ldx}, 1, st, "Du");
     if (rc) return rc;
   }
@@ -340,13 +372,13 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     g.M = R, g.N = p.H[l], g.Nb = p.H[l], g.kchunk = 0;
     if (l == 1) {
       g.nseg = 1;
-      g.seg[0] = GemmSeg{ws + p.V, n.W[1], p.ldx, p.d_in, p.d_in};
+      g.seg[0] = GemmSeg{ws + p.V, n.W[1], p.ldx, p.ldw, p.kin};
     } else {
       g.nseg = 1;
       g.seg[0] = GemmSeg{ws + p.hd[l - 1], n.W[l], p.H[l - 1], p.H[l - 1], p.H[l - 1]};
       if (p.nais) {
         g.nseg = 2;
-        g.seg[1] = GemmSeg{ws + p.V, n.Win[l], p.ldx, p.d_in, p.d_in};
+        g.seg[1] = GemmSeg{ws + p.V, n.Win[l], p.ldx, p.ldw, p.kin};
       }
     }
     EpiTan e{};
@@ -396,7 +428,7 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
       GemmArgs g{};
       g.M = H, g.N = H, g.Nb = H, g.kchunk = 0, g.nseg = 1;
       g.seg[0] = GemmSeg{n.Wraw[l], ws + p.Sm[l], H, H, H};
-      rc = dense<true, false>(s, g, EpiStore{grads + s->off_W[l], H}, 1, st, "nais Wbar");
+      rc = dense<true, false>(s, g, EpiStore{grads + s->off_W[l], H}, 1, st, "nais Wbar", false);
       if (rc) return rc;
     }
   }
@@ -448,7 +480,7 @@ static int gen_increments(const FbsnnSpec* s, const Plan& p, float* ws, long lon
     GemmArgs g{};
     g.M = (int)p.rows, g.N = p.ldi, g.Nb = s->D, g.kchunk = 0, g.nseg = 1;
     g.seg[0] = GemmSeg{ws + p.zraw, chol, p.ldi, s->D, s->D};
-    int rc = dense<true, true>(s, g, EpiStore{ws + p.inc, p.ldi}, 1, st, "chol");
+    int rc = dense<true, true>(s, g, EpiStore{ws + p.inc, p.ldi}, 1, st, "chol", false);
     if (rc) return rc;
   }
   return 0;
@@ -473,6 +505,7 @@ static int loss_grad_impl(const FbsnnSpec* s, const float* params, float* grads,
   if (rc) return rc;
   float* ws = (float*)workspace;
   const Net n = bind_net(s, p, params, ws);
+  if ((rc = prepare_weights(s, p, params, ws, st))) return rc;
   if (p.nais && (rc = nais_prepare(s, p, n, ws, st))) return rc;
   if (!W && (rc = gen_increments(s, p, ws, M, T, path_offset, seed, iteration, iter_dev, chol, st))) return rc;
   {
@@ -538,6 +571,32 @@ int fbsnn_dense_timing_read(double* out6) {
   return 0;
 }
 
+// Test hook: one dense GEMM C = A * B with a plain store epilogue, on the SIMT or the tcgen05 kernel.
+//   a_kc: A[m*lda + k] (1) or A[k*lda + m] (0);  b_kc: B[n*ldb + k] (1) or B[k*ldb + n] (0)
+int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const float* A, int lda, const float* B,
+                     int ldb, float* C, int ldc, void* stream) {
+  GemmArgs g{};
+  g.nseg = 1, g.M = M, g.N = N, g.Nb = N, g.kchunk = 0;
+  g.seg[0] = GemmSeg{A, B, lda, ldb, K};
+  const EpiStore e{C, ldc};
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t err;
+  if (use_tc) {
+    bool ok = a_kc && b_kc ? tc_eligible<true, true>(g, 1) : (a_kc ? tc_eligible<true, false>(g, 1) : tc_eligible<false, false>(g, 1));
+    if (!ok || (!a_kc && b_kc)) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
+    if (a_kc && b_kc) err = launch_gemm_tc<true, true>(g, e, 1, num_sms(), st);
+    else if (a_kc) err = launch_gemm_tc<true, false>(g, e, 1, num_sms(), st);
+    else err = launch_gemm_tc<false, false>(g, e, 1, num_sms(), st);
+  } else {
+    if (a_kc && b_kc) err = launch_gemm<true, true>(g, e, 1, num_sms(), st);
+    else if (a_kc) err = launch_gemm<true, false>(g, e, 1, num_sms(), st);
+    else if (!b_kc) err = launch_gemm<false, false>(g, e, 1, num_sms(), st);
+    else return fail(FBSNN_E_UNSUPPORTED, "layout");
+  }
+  if (err != cudaSuccess) return fail(FBSNN_E_CUDA, "debug gemm: %s", cudaGetErrorString(err));
+  return 0;
+}
+
 int fbsnn_workspace_bytes(const FbsnnSpec* spec, int64_t n_paths, int with_grad, size_t* bytes_out) {
   int rc = validate(spec);
   if (rc) return rc;
@@ -577,6 +636,7 @@ int fbsnn_net_u(const FbsnnSpec* spec, const float* params, const float* t, cons
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   const Net n = bind_net(spec, p, params, ws);
+  if ((rc = prepare_weights(spec, p, params, ws, st))) return rc;
   if (p.nais && (rc = nais_prepare(spec, p, n, ws, st))) return rc;
   const long long tot = rows * p.ldx;
   pack_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(t, X, rows, spec->D, p.ldx, ws + p.xin);

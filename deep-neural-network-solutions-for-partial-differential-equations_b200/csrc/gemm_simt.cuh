@@ -29,8 +29,18 @@ struct GemmArgs {
 // ----------------------------------------------------------------------------------------------------
 // epilogues: operator()(row, col, acc4) with col % 4 == 0 and col + 3 < N
 // ----------------------------------------------------------------------------------------------------
+// Every epilogue is split in two so that the tcgen05 kernel can issue the loads of a whole 32-column chunk
+// before consuming them:  Frag f = prefetch(r, c)  reads the row-array inputs,  finish(r, c, acc, f)  computes
+// and stores.  operator() = finish(prefetch) for the SIMT kernel.
+struct Frag3 {
+  float4 x, y, z;
+};
+#define FBSNN_EPI_CALL                                                                                   \
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const { finish(r, c, v, prefetch(r, c)); }
+
 // F sweep: z = acc + bias;  g = act(z), a = act'(z);  h = g (+ h_prev);  last layer also seeds the adjoint
 struct EpiFwd {
+  typedef Frag3 Frag;
   const float* bias1;
   const float* bias2;  // nullable (NAIS: layer{l}_input.bias)
   const float* res;    // nullable: h_{l-1} (NAIS residual stream)
@@ -41,35 +51,40 @@ struct EpiFwd {
   float* delta;
   float* s;            // nullable (forward-only mode)
   int ld, act;
-  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
-    const float4 b1 = ld4(bias1 + c);
-    float z[4] = {v.x + b1.x, v.y + b1.y, v.z + b1.z, v.w + b1.w};
+  __device__ __forceinline__ Frag prefetch(int r, int c) const {
+    Frag f;
+    f.x = ld4(bias1 + c);
     if (bias2) {
       const float4 b2 = ld4(bias2 + c);
-      z[0] += b2.x, z[1] += b2.y, z[2] += b2.z, z[3] += b2.w;
+      f.x.x += b2.x, f.x.y += b2.y, f.x.z += b2.z, f.x.w += b2.w;
     }
+    f.y = h ? ld4(res + (size_t)r * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    f.z = wout ? ld4(wout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return f;
+  }
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
+    const float z[4] = {v.x + f.x.x, v.y + f.x.y, v.z + f.x.z, v.w + f.x.w};
     float gv[4], av[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) act_ga(act, z[i], gv[i], av[i]);
     const size_t o = (size_t)r * ld + c;
     st4(g + o, make_float4(gv[0], gv[1], gv[2], gv[3]));
     st4(a + o, make_float4(av[0], av[1], av[2], av[3]));
-    if (h) {
-      const float4 p = ld4(res + o);
-      st4(h + o, make_float4(gv[0] + p.x, gv[1] + p.y, gv[2] + p.z, gv[3] + p.w));
-    }
+    if (h) st4(h + o, make_float4(gv[0] + f.y.x, gv[1] + f.y.y, gv[2] + f.y.z, gv[3] + f.y.w));
     if (wout) {
-      const float4 w = ld4(wout + c);
+      const float4 w = f.z;
       st4(delta + o, make_float4(w.x * av[0], w.y * av[1], w.z * av[2], w.w * av[3]));
       if (s)
         st4(s + o, make_float4(w.x * act_c(act, gv[0], av[0]), w.y * act_c(act, gv[1], av[1]),
                                w.z * act_c(act, gv[2], av[2]), w.w * act_c(act, gv[3], av[3])));
     }
   }
+  FBSNN_EPI_CALL
 };
 
 // A sweep (writes layer l-1): ht = acc (+ ht_l | + wout);  delta = ht * a;  s = ht * c
 struct EpiAdj {
+  typedef Frag3 Frag;
   const float* a;
   const float* g;
   const float* res;       // nullable: ht_l (NAIS)
@@ -78,29 +93,30 @@ struct EpiAdj {
   float* delta;
   float* s;               // nullable (forward-only mode)
   int ld, act;
-  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+  __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
-    float ht[4] = {v.x, v.y, v.z, v.w};
-    if (res) {
-      const float4 p = ld4(res + o);
-      ht[0] += p.x, ht[1] += p.y, ht[2] += p.z, ht[3] += p.w;
-    } else if (res_head) {
-      const float4 p = ld4(res_head + c);
-      ht[0] += p.x, ht[1] += p.y, ht[2] += p.z, ht[3] += p.w;
-    }
-    const float4 av = ld4(a + o);
+    Frag f;
+    f.x = ld4(a + o);
+    f.y = s ? ld4(g + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    f.z = res ? ld4(res + o) : (res_head ? ld4(res_head + c) : make_float4(0.f, 0.f, 0.f, 0.f));
+    return f;
+  }
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
+    const size_t o = (size_t)r * ld + c;
+    const float ht[4] = {v.x + f.z.x, v.y + f.z.y, v.z + f.z.z, v.w + f.z.w};
+    const float4 av = f.x, gv = f.y;
     st4(delta + o, make_float4(ht[0] * av.x, ht[1] * av.y, ht[2] * av.z, ht[3] * av.w));
-    if (s) {
-      const float4 gv = ld4(g + o);
+    if (s)
       st4(s + o, make_float4(ht[0] * act_c(act, gv.x, av.x), ht[1] * act_c(act, gv.y, av.y),
                              ht[2] * act_c(act, gv.z, av.z), ht[3] * act_c(act, gv.w, av.w)));
-    }
     if (ht_out) st4(ht_out + o, make_float4(ht[0], ht[1], ht[2], ht[3]));
   }
+  FBSNN_EPI_CALL
 };
 
 // T sweep (layer l): dbar = acc;  hd = dbar * a (+ hd_{l-1});  zz = dbar * s;  last layer: zbar = ybar*wout*a + zz
 struct EpiTan {
+  typedef Frag3 Frag;
   const float* a;
   float* s_zz;        // in: s, out: zz (or zbar for the last layer)
   const float* res;   // nullable: hd_{l-1}
@@ -108,16 +124,19 @@ struct EpiTan {
   const float* ybar;  // nullable: last layer
   const float* wout;
   int ld;
-  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+  __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
-    const float4 av = ld4(a + o);
-    const float4 sv = ld4(s_zz + o);
-    float hdv[4] = {v.x * av.x, v.y * av.y, v.z * av.z, v.w * av.w};
+    Frag f;
+    f.x = ld4(a + o);
+    f.y = ld4(s_zz + o);
+    f.z = res ? ld4(res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return f;
+  }
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
+    const size_t o = (size_t)r * ld + c;
+    const float4 av = f.x, sv = f.y;
+    const float hdv[4] = {v.x * av.x + f.z.x, v.y * av.y + f.z.y, v.z * av.z + f.z.z, v.w * av.w + f.z.w};
     float zz[4] = {v.x * sv.x, v.y * sv.y, v.z * sv.z, v.w * sv.w};
-    if (res) {
-      const float4 p = ld4(res + o);
-      hdv[0] += p.x, hdv[1] += p.y, hdv[2] += p.z, hdv[3] += p.w;
-    }
     if (wout) {
       const float yb = ybar[r];
       const float4 w = ld4(wout + c);
@@ -126,10 +145,12 @@ struct EpiTan {
     st4(hd + o, make_float4(hdv[0], hdv[1], hdv[2], hdv[3]));
     st4(s_zz + o, make_float4(zz[0], zz[1], zz[2], zz[3]));
   }
+  FBSNN_EPI_CALL
 };
 
 // B sweep (writes layer l-1): hb = acc (+ hb_l | + ybar*wout);  zbar = hb * a + zz
 struct EpiBwd {
+  typedef Frag3 Frag;
   const float* a;
   float* zz_zbar;
   const float* res;   // nullable: hb_l (NAIS, l < L)
@@ -137,37 +158,55 @@ struct EpiBwd {
   const float* wout;
   float* hb_out;      // nullable
   int ld;
-  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+  __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
-    float hb[4] = {v.x, v.y, v.z, v.w};
+    Frag f;
+    f.x = ld4(a + o);
+    f.y = ld4(zz_zbar + o);
     if (res) {
-      const float4 p = ld4(res + o);
-      hb[0] += p.x, hb[1] += p.y, hb[2] += p.z, hb[3] += p.w;
+      f.z = ld4(res + o);
     } else if (ybar) {
       const float yb = ybar[r];
       const float4 w = ld4(wout + c);
-      hb[0] += yb * w.x, hb[1] += yb * w.y, hb[2] += yb * w.z, hb[3] += yb * w.w;
+      f.z = make_float4(yb * w.x, yb * w.y, yb * w.z, yb * w.w);
+    } else {
+      f.z = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float4 av = ld4(a + o);
-    const float4 zz = ld4(zz_zbar + o);
+    return f;
+  }
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
+    const size_t o = (size_t)r * ld + c;
+    const float hb[4] = {v.x + f.z.x, v.y + f.z.y, v.z + f.z.z, v.w + f.z.w};
+    const float4 av = f.x, zz = f.y;
     st4(zz_zbar + o, make_float4(hb[0] * av.x + zz.x, hb[1] * av.y + zz.y, hb[2] * av.z + zz.z, hb[3] * av.w + zz.w));
     if (hb_out) st4(hb_out + o, make_float4(hb[0], hb[1], hb[2], hb[3]));
   }
+  FBSNN_EPI_CALL
 };
 
+struct FragNone {};
 struct EpiStore {
+  typedef FragNone Frag;
   float* out;
   int ld;
-  __device__ __forceinline__ void operator()(int r, int c, float4 v) const { st4(out + (size_t)r * ld + c, v); }
+  __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&) const { st4(out + (size_t)r * ld + c, v); }
+  FBSNN_EPI_CALL
 };
 
-// split-K partial tile: out[z][M][N]
+// split-K partial tile: out[z][M][N]; `z` is blockIdx.z in the SIMT kernel, the split index in the tcgen05 kernel
 struct EpiPartial {
+  typedef FragNone Frag;
   float* out;
   int M, N;
-  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {
+  __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&) const {
     st4(out + ((size_t)blockIdx.z * M + r) * N + c, v);
   }
+  __device__ __forceinline__ void finish_split(int split, int r, int c, float4 v) const {
+    st4(out + ((size_t)split * M + r) * N + c, v);
+  }
+  FBSNN_EPI_CALL
 };
 
 // ----------------------------------------------------------------------------------------------------

@@ -131,6 +131,14 @@ __global__ void pack_rows_kernel(const float* t, const float* X, long long rows,
   xin[i] = c == 0 ? t[r] : (c <= D ? X[r * D + c - 1] : 0.f);
 }
 
+// dst (rows x ldd) = [src (rows x cols) | 0]   (TF32 variant: zero-padded homes of the input-width matrices)
+__global__ void pad_copy_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst, int ldd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ldd) return;
+  const int r = i / ldd, c = i % ldd;
+  dst[i] = c < cols ? src[r * cols + c] : 0.f;
+}
+
 // u[r] = h_L[r,:] . wout + bout      (one warp per row)
 __global__ void head_kernel(const float* __restrict__ h, int ld, int H, const float* __restrict__ wout,
                             const float* __restrict__ bout, long long rows, float* __restrict__ u) {

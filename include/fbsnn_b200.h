@@ -71,6 +71,11 @@ long long fbsnn_launch_count(void);
 void fbsnn_dense_timing(int enable);
 int fbsnn_dense_timing_read(double* out6);
 
+/* Test hook (tests/test_gemm_gpu.py): one dense GEMM with a plain store on the SIMT (use_tc = 0) or tcgen05 kernel.
+ * a_kc: A[m*lda + k] (1) | A[k*lda + m] (0);  b_kc: B[n*ldb + k] (1) | B[k*ldb + n] (0);  C[m*ldc + n]. */
+int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const float* A, int lda, const float* B,
+                     int ldb, float* C, int ldc, void* stream);
+
 /* Bytes of device scratch needed for `n_paths` paths (rows = n_paths * (N+1)).  `with_grad` = 0 sizes for
  * forward/predict only. */
 int fbsnn_workspace_bytes(const FbsnnSpec* spec, int64_t n_paths, int with_grad, size_t* bytes_out);

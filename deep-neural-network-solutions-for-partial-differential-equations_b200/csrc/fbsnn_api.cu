@@ -108,7 +108,7 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   p.col_rows_per_block = (int)((rows + p.col_blocks - 1) / p.col_blocks);
   p.col_blocks = (int)((rows + p.col_rows_per_block - 1) / p.col_rows_per_block);
   int split = (int)std::min<long long>(std::max<long long>((rows + 511) / 512, 1), 256);
-  p.wg_chunk = round_up((rows + split - 1) / split, 16);
+  p.wg_chunk = round_up((rows + split - 1) / split, 32);   // multiple of the tcgen05 kernel's BLOCK_K
   p.wg_split = (int)((rows + p.wg_chunk - 1) / p.wg_chunk);
   p.gsq_blocks = 256;
   size_t off = 0;

@@ -12,8 +12,10 @@
 //              sweep epilogue functors as the SIMT kernel, reading/writing the row arrays with 16-byte accesses.
 // Operand layouts in shared memory are the canonical UMMA SWIZZLE_128B ones:
 //   K-major  (activation rows, weights used as W^T): rows x 32 tf32 (128 B), SBO = 1024 B, k-step = +32 B
-//   MN-major (weights used as W, weight-gradient operands): chunks of [32 k-rows x 32 elements], LBO = 4096 B
-//             between 32-element chunks, SBO = 1024 B between 8-row groups, k-step = +1024 B
+//   MN-major (weights used as W, weight-gradient operands): 32-bit MN-major operands only exist in the
+//             "128B swizzle, 32B atom" mode (TMA SWIZZLE_128B_ATOM_32B, descriptor layout type 1): chunks of
+//             [32 k-rows x 32 elements], LBO = 4096 B between 32-element chunks, SBO = 512 B between 4-row groups,
+//             k-step (8 rows) = +1024 B
 #pragma once
 #include <cuda.h>
 
@@ -79,14 +81,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version bit set
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor, Blackwell version bit set.  layout: 2 = SWIZZLE_128B (K-major operands),
+// 1 = SWIZZLE_128B_BASE32B (the only layout for MN-major 32-bit operands)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // instruction descriptor: D = f32, A = B = tf32, M = 128
@@ -206,8 +209,8 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
             const uint32_t b = smem_u32(sB + stage * B_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adesc = A_MN ? make_desc(a + k * 1024, 4096, 1024) : make_desc(a + k * 32, 16, 1024);
-              const uint64_t bdesc = B_MN ? make_desc(b + k * 1024, 4096, 1024) : make_desc(b + k * 32, 16, 1024);
+              const uint64_t adesc = A_MN ? make_desc(a + k * 1024, 4096, 512, 1) : make_desc(a + k * 32, 16, 1024, 2);
+              const uint64_t bdesc = B_MN ? make_desc(b + k * 1024, 4096, 512, 1) : make_desc(b + k * 32, 16, 1024, 2);
               umma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -282,7 +285,7 @@ inline EncodeTiledFn encode_fn() {
 }
 // 2-D fp32 tensor map over X[outer x inner] (inner contiguous, leading dimension ld), 128-byte swizzle.
 inline bool make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_inner,
-                     int box_outer) {
+                     int box_outer, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -290,7 +293,8 @@ inline bool make_map(CUtensorMap* m, const float* base, long long inner, long lo
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+            mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
          CUDA_SUCCESS;
 }
 
@@ -317,10 +321,10 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit,
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
     bool ok;
-    if (A_MN) ok = tc::make_map(&tm.a[s], sg.A, g.M, sg.K, sg.lda, 32, 32);      // P[k = rows][m]
-    else      ok = tc::make_map(&tm.a[s], sg.A, sg.K, g.M, sg.lda, 32, tc::BM);  // X[m = rows][k]
-    if (B_MN) ok = ok && tc::make_map(&tm.b[s], sg.B, g.Nb, sg.K, sg.ldb, 32, 32);   // W[k][n] / Q[k = rows][n]
-    else      ok = ok && tc::make_map(&tm.b[s], sg.B, sg.K, g.Nb, sg.ldb, 32, g.N);  // W[n][k]
+    if (A_MN) ok = tc::make_map(&tm.a[s], sg.A, g.M, sg.K, sg.lda, 32, 32, true);       // P[k = rows][m]
+    else      ok = tc::make_map(&tm.a[s], sg.A, sg.K, g.M, sg.lda, 32, tc::BM, false);  // X[m = rows][k]
+    if (B_MN) ok = ok && tc::make_map(&tm.b[s], sg.B, g.Nb, sg.K, sg.ldb, 32, 32, true);    // W[k][n] / Q[k = rows][n]
+    else      ok = ok && tc::make_map(&tm.b[s], sg.B, sg.K, g.Nb, sg.ldb, 32, g.N, false);  // W[n][k]
     if (!ok) return cudaErrorInvalidValue;
   }
   for (int s = g.nseg; s < 4; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];

@@ -191,7 +191,7 @@ def setup(args):
     return c
 
 
-def make_solver(c, args):
+def make_solver(c, args, batches=None):
     """Solver + `nbatch` resident synthetic minibatches (reference layout), generated on the device by Philox."""
     import ctypes
     pde = c.pde
@@ -203,6 +203,8 @@ def make_solver(c, args):
     m_loc = hi - lo
     sp = sol._spec()
     ws = sol._workspace(c.lib, sp, m_loc, True)
+    if batches is not None:
+        return sol, batches, m_loc
     batches = []
     for b in range(2):
         t = torch.empty(m_loc, NSTEPS + 1, 1, device=c.dev)
@@ -246,19 +248,25 @@ def measure_roofline(c, args, sol, batches, ms_per_step, m_loc):
     c.lib.fbsnn_dense_timing(1)
     sol.training_step(*batches[0], loss)
     torch.cuda.synchronize()
-    out6 = (ctypes.c_double * 6)()
-    c.pde._lib.check(c.lib.fbsnn_dense_timing_read(out6), "timing")
+    out = (ctypes.c_double * 8)()
+    c.pde._lib.check(c.lib.fbsnn_dense_timing_read(out), "timing")
     c.lib.fbsnn_dense_timing(0)
-    n_dense, dense_ms, dense_flops = int(out6[0]), out6[1], out6[2]
-    achieved = dense_flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
-    tc_peak = pk["bf16"] * 0.5          # kind::tf32 issues at half the bf16 rate (nominal 1.1 vs 2.25 PFLOP/s)
-    return {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+    n_dense, dense_ms, dense_flops, dense_bytes = int(out[0]), out[1], out[2], out[6]
+    tflops = dense_flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
+    gbs = dense_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
+    tf32_peak = pk["bf16"] * 0.5          # kind::tf32 issues at half the bf16 rate (nominal 1.1 vs 2.25 PFLOP/s)
+    is_tc = out[3] > 0
+    # The dense-layer kernel moves 3-5 row arrays per 2*256*256 FLOP per row (26-43 FLOP/B, ridge ~130 FLOP/B for
+    # TF32), so on the tcgen05 variant it is HBM-bound: report it against the measured copy bandwidth.  The SIMT
+    # fp32 variant is FMA-issue bound; it is reported against the same HBM peak for comparability, with the FLOP
+    # rates alongside ("Roofline").
+    return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
             "traffic": None,
-            "kernel": "gemm_tc_kernel (tcgen05 kind::tf32)" if out6[3] > 0 else "gemm_simt_kernel (fp32 FMA)",
+            "kernel": "gemm_tc_kernel (tcgen05 kind::tf32, TMA, TMEM)" if is_tc else "gemm_simt_kernel (fp32 FMA)",
             "launches_per_step": n_dense, "dense_ms_per_step": dense_ms, "dense_share_of_step": dense_ms / ms_per_step,
-            "tc_launches": int(out6[3]), "tc_ms": out6[4],
-            "tc_tflops": (out6[5] / (out6[4] * 1e-3) / 1e12) if out6[4] > 0 else None,
-            "peak_source": f"{pk['source']} bf16 {pk['bf16']} TFLOP/s x 0.5 (tf32 rate)",
+            "algorithmic_bytes_per_step": dense_bytes, "tflops": tflops, "tf32_peak_tflops": tf32_peak,
+            "tensor_frac": tflops / tf32_peak, "tc_launches": int(out[3]),
+            "peak_source": f"{pk['source']}: HBM copy {pk['hbm']} GB/s; bf16 {pk['bf16']} TFLOP/s x 0.5 for tf32",
             "step_tflops": FLOP_PER_ROW * m_loc * (NSTEPS + 1) / (ms_per_step * 1e-3) / 1e12}
 
 
@@ -348,7 +356,18 @@ def run_ours(args):
     line["roofline"] = measure_roofline(c, args, sol, batches, ms_per_step, m_loc)
     if not args.skip_e2e:
         line["e2e"] = measure_e2e(c, args, sol, batches)
-    del sol, batches
+    del sol
+    torch.cuda.empty_cache()
+    if args.precision == "tf32" and not args.skip_fp32:
+        # the parity-grade fp32 SIMT variant on the same workload, fewer steps (it is ~4x slower)
+        a2 = argparse.Namespace(**vars(args))
+        a2.precision, a2.steps = "fp32", max(2, args.steps // 3)
+        sol2, _, _ = make_solver(c, a2, batches)
+        ms2, _, _, _ = measure_value(c, a2, sol2, batches)
+        line["fp32_variant"] = {"value": 1e3 / ms2, "unit": "iters/s", "ms_per_step": ms2, "steps": a2.steps,
+                                "kernel": "gemm_simt_kernel (fp32 FMA), tolerances of tests/test_parity_gpu.py::TOL"}
+        del sol2
+    del batches
     torch.cuda.empty_cache()
     if not args.skip_mc:
         line["mc"] = measure_mc(c, args)
@@ -376,11 +395,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=65536, help="global number of Brownian paths M")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 tensor-core variant (stated tolerance, tests/test_parity_gpu.py); "
+                         "fp32: SIMT parity-grade variant")
     ap.add_argument("--mc-paths", type=int, default=1 << 28)
     ap.add_argument("--cpu-sample-paths", type=int, default=256)
     ap.add_argument("--skip-mc", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-fp32", action="store_true", help="do not also time the fp32 SIMT variant")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (the JSON line then has no e2e)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -180,7 +180,7 @@ constexpr int kMaxTimed = 4096;
 static bool g_timing = false;
 static int g_ntimed = 0;
 static cudaEvent_t g_ev0[kMaxTimed], g_ev1[kMaxTimed];
-static double g_flops[kMaxTimed];
+static double g_flops[kMaxTimed], g_bytes[kMaxTimed];
 static bool g_timed_tc[kMaxTimed];
 
 // dense layer dispatch: SIMT fp32, or tcgen05 TF32 when the variant is selected and the shape qualifies
@@ -195,6 +195,8 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
     double k = 0;
     for (int i = 0; i < g.nseg; ++i) k += g.seg[i].K;
     g_flops[slot] = 2.0 * (double)g.M * (double)g.N * k;   // algorithmic FLOPs of this launch (padding included in N)
+    // algorithmic HBM bytes: both operands once + every row array the fused epilogue reads or writes
+    g_bytes[slot] = 4.0 * (k * ((double)g.M + (double)g.N) + (double)g.M * (double)g.N * epi.io_arrays() * nsplit);
     g_timed_tc[slot] = tc;
     cudaEventRecord(g_ev0[slot], st);
   }
@@ -271,7 +273,9 @@ static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* 
 // F and A sweeps over `rows` rows whose inputs are already in ws[xin]; leaves Y in ws[Y], Du_full in ws[zf].
 static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, bool with_grad, cudaStream_t st) {
   const int R = (int)p.rows;
-  const int act = s->act_kind;
+  int act = s->act_kind;
+  if (p.tf32 && act == FBSNN_ACT_SINE) act = kActSineFast;
+  if (p.tf32 && act == FBSNN_ACT_TANH) act = kActTanhFast;
   for (int l = 1; l <= p.L; ++l) {
     GemmArgs g{};
     g.M = R, g.N = p.H[l], g.Nb = p.H[l], g.kchunk = 0;
@@ -558,15 +562,15 @@ int fbsnn_version(void) { return 100; }
 long long fbsnn_launch_count(void) { return g_launches; }
 void fbsnn_dense_timing(int enable) { g_timing = enable != 0; g_ntimed = 0; }
 // Sums the recorded dense-layer launches (caller has synchronised): out = {n_launches, total ms, total FLOPs,
-// n tcgen05 launches, tcgen05 ms, tcgen05 FLOPs}.
-int fbsnn_dense_timing_read(double* out6) {
-  if (!out6) return FBSNN_E_BADARG;
-  for (int i = 0; i < 6; ++i) out6[i] = 0;
+// n tcgen05 launches, tcgen05 ms, tcgen05 FLOPs, total algorithmic bytes, tcgen05 algorithmic bytes}.
+int fbsnn_dense_timing_read(double* out8) {
+  if (!out8) return FBSNN_E_BADARG;
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
   for (int i = 0; i < g_ntimed; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, g_ev0[i], g_ev1[i]) != cudaSuccess) return fail(FBSNN_E_CUDA, "event not complete");
-    out6[0] += 1, out6[1] += ms, out6[2] += g_flops[i];
-    if (g_timed_tc[i]) out6[3] += 1, out6[4] += ms, out6[5] += g_flops[i];
+    out8[0] += 1, out8[1] += ms, out8[2] += g_flops[i], out8[6] += g_bytes[i];
+    if (g_timed_tc[i]) out8[3] += 1, out8[4] += ms, out8[5] += g_flops[i], out8[7] += g_bytes[i];
   }
   return 0;
 }

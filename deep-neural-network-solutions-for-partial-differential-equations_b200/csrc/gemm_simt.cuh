@@ -51,6 +51,8 @@ struct EpiFwd {
   float* delta;
   float* s;            // nullable (forward-only mode)
   int ld, act;
+  // number of (rows x N) fp32 arrays this epilogue reads + writes (algorithmic HBM traffic, bench.py roofline)
+  int io_arrays() const { return 2 + (h ? 2 : 0) + (wout ? (s ? 2 : 1) : 0); }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     Frag f;
     f.x = ld4(bias1 + c);
@@ -93,6 +95,7 @@ struct EpiAdj {
   float* delta;
   float* s;               // nullable (forward-only mode)
   int ld, act;
+  int io_arrays() const { return 2 + (s ? 2 : 0) + (res ? 1 : 0) + (ht_out ? 1 : 0); }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
     Frag f;
@@ -124,6 +127,7 @@ struct EpiTan {
   const float* ybar;  // nullable: last layer
   const float* wout;
   int ld;
+  int io_arrays() const { return 4 + (res ? 1 : 0); }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
     Frag f;
@@ -158,6 +162,7 @@ struct EpiBwd {
   const float* wout;
   float* hb_out;      // nullable
   int ld;
+  int io_arrays() const { return 3 + (res ? 1 : 0) + (hb_out ? 1 : 0); }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
     Frag f;
@@ -189,6 +194,7 @@ struct EpiStore {
   typedef FragNone Frag;
   float* out;
   int ld;
+  int io_arrays() const { return 1; }
   __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
   __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&) const { st4(out + (size_t)r * ld + c, v); }
   FBSNN_EPI_CALL
@@ -199,6 +205,7 @@ struct EpiPartial {
   typedef FragNone Frag;
   float* out;
   int M, N;
+  int io_arrays() const { return 1; }
   __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
   __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&) const {
     st4(out + ((size_t)blockIdx.z * M + r) * N + c, v);

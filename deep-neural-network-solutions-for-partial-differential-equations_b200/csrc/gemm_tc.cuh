@@ -26,12 +26,15 @@
 namespace fbsnn {
 namespace tc {
 
-constexpr int BM = 128, BK = 32, STAGES = 4, UMMA_K = 8;
+constexpr int BM = 128, BK = 32, STAGES = 3, UMMA_K = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 4;       // 16 KB
 constexpr int B_STAGE_BYTES = 256 * BK * 4;      // 32 KB (N <= 256)
 constexpr int NUM_THREADS = 320;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 36;                                      // padded row of the per-warp 32x32 transpose tile
+constexpr int EPI_TILE_BYTES = 32 * EPI_LD * 4;                 // 4.5 KB per epilogue warp
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_EPI_WARPS * EPI_TILE_BYTES +
+                           1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t kSpinLimit = 1u << 24;       // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct TmSet {
@@ -124,7 +127,8 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  float* epi_tiles = (float*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_EPI_WARPS * EPI_TILE_BYTES);
   uint64_t* full = bars;               // [STAGES]
   uint64_t* empty = bars + STAGES;     // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES; // [2]
@@ -223,9 +227,14 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
     }
   } else {
     // ===================== epilogue warps =====================
+    // TMEM hands each lane one accumulator ROW; the row arrays in global memory want a warp on one row's
+    // contiguous columns.  Each 32x32 chunk is therefore transposed through a warp-private padded smem tile, after
+    // which 8 lanes cover 128 B of one row and a warp-wide access touches 4 full cache lines instead of 32 partial.
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;      // column half
     const int ncol = N >> 1;
+    float* tile = epi_tiles + (warp - 2) * (32 * EPI_LD);
+    const int sub = lane >> 3, cc = (lane & 7) * 4;
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int mt = w % num_mtiles;
@@ -234,24 +243,37 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
-      const int r = mt * BM + q * 32 + lane;
+      const int r0 = mt * BM + q * 32;
       for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c0;
         FBSNN_TMEM_LD32(taddr, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (r < g.M) {
-          typename Epi::Frag f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = epi.prefetch(r, c0 + 4 * j);
+        for (int j = 0; j < 8; ++j)
+          st4(tile + lane * EPI_LD + 4 * j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 a4 = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            if constexpr (std::is_same<Epi, EpiPartial>::value) epi.finish_split(split, r, c0 + 4 * j, a4);
-            else epi.finish(r, c0 + 4 * j, a4, f[j]);
+        for (int ib = 0; ib < 2; ++ib) {
+          typename Epi::Frag f[4];
+          float4 a4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (ib * 4 + i) * 4 + sub;
+            if (r0 + rr < g.M) f[i] = epi.prefetch(r0 + rr, c0 + cc);
+            a4[i] = ld4(tile + rr * EPI_LD + cc);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (ib * 4 + i) * 4 + sub;
+            if (r0 + rr < g.M) {
+              if constexpr (std::is_same<Epi, EpiPartial>::value) epi.finish_split(split, r0 + rr, c0 + cc, a4[i]);
+              else epi.finish(r0 + rr, c0 + cc, a4[i], f[i]);
+            }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

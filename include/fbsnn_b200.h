@@ -66,10 +66,11 @@ const char* fbsnn_last_error(void);
 int fbsnn_version(void);
 /* Measurement hooks used by bench.py: number of kernels this library has launched since it was loaded; and
  * optional CUDA-event timing of every dense-layer launch (enable, run, synchronise, read).
- * out6 = {launches, ms, algorithmic FLOPs, tcgen05 launches, tcgen05 ms, tcgen05 FLOPs}. */
+ * out8 = {launches, ms, algorithmic FLOPs, tcgen05 launches, tcgen05 ms, tcgen05 FLOPs, algorithmic HBM bytes,
+ * tcgen05 algorithmic HBM bytes} (bytes = both operands once + every row array the fused epilogue touches). */
 long long fbsnn_launch_count(void);
 void fbsnn_dense_timing(int enable);
-int fbsnn_dense_timing_read(double* out6);
+int fbsnn_dense_timing_read(double* out8);
 
 /* Test hook (tests/test_gemm_gpu.py): one dense GEMM with a plain store on the SIMT (use_tc = 0) or tcgen05 kernel.
  * a_kc: A[m*lda + k] (1) | A[k*lda + m] (0);  b_kc: B[n*ldb + k] (1) | B[k*ldb + n] (0);  C[m*ldc + n]. */

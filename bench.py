@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=65536, help="global number of Brownian paths M")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32x3"],
                     help="tf32: tcgen05 tensor-core variant (stated tolerance, tests/test_parity_gpu.py); "
                          "fp32: SIMT parity-grade variant")
     ap.add_argument("--mc-paths", type=int, default=1 << 28)

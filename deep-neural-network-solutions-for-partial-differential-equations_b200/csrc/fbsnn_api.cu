@@ -84,7 +84,7 @@ static int validate(const FbsnnSpec* s) {
   if (s->mu_kind < 0 || s->mu_kind > 1 || s->sigma_kind < 0 || s->sigma_kind > 1 || s->phi_kind < 0 ||
       s->phi_kind > 2 || s->g_kind < 0 || s->g_kind > 3)
     return fail(FBSNN_E_UNSUPPORTED, "problem callables outside the closed enumeration");
-  if (s->precision != FBSNN_PREC_FP32 && s->precision != FBSNN_PREC_TF32)
+  if (s->precision != FBSNN_PREC_FP32 && s->precision != FBSNN_PREC_TF32 && s->precision != FBSNN_PREC_TF32X3)
     return fail(FBSNN_E_UNSUPPORTED, "unknown precision %d", s->precision);
   return 0;
 }
@@ -93,7 +93,7 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   memset(&p, 0, sizeof(p));
   p.D = s->D, p.N = s->N, p.L = s->n_hidden;
   p.d_in = s->D + 1;
-  p.tf32 = s->precision == FBSNN_PREC_TF32;
+  p.tf32 = s->precision != FBSNN_PREC_FP32;   // both tensor-core variants use the padded (UMMA-tileable) layout
   // TF32 variant: the input width is zero-padded to a multiple of 32 so that every dense layer is a TMA/UMMA tile
   p.ldx = round_up(p.d_in, p.tf32 ? 32 : 4);
   p.kin = p.tf32 ? p.ldx : p.d_in;
@@ -107,7 +107,10 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   p.col_blocks = (int)std::min<long long>(std::max<long long>((rows + 63) / 64, 1), 1024);
   p.col_rows_per_block = (int)((rows + p.col_blocks - 1) / p.col_blocks);
   p.col_blocks = (int)((rows + p.col_rows_per_block - 1) / p.col_rows_per_block);
+  // split-K of the weight-gradient contraction: the SIMT kernel wants many CTAs; the persistent tcgen05 kernel
+  // wants (M tiles) x splits ~ one work item per SM, and fewer partial tiles to reduce afterwards
   int split = (int)std::min<long long>(std::max<long long>((rows + 511) / 512, 1), 256);
+  if (s->precision != FBSNN_PREC_FP32) split = (int)std::min<long long>(std::max<long long>((rows + 63) / 64, 1), 74);
   p.wg_chunk = round_up((rows + split - 1) / split, 32);   // multiple of the tcgen05 kernel's BLOCK_K
   p.wg_split = (int)((rows + p.wg_chunk - 1) / p.wg_chunk);
   p.gsq_blocks = 256;
@@ -155,7 +158,7 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
       wg = std::max(wg, (size_t)p.H[l] * (size_t)p.ldx);
     }
     p.part_wg = take(wg * p.wg_split);
-    p.part_col = take((size_t)kMaxColJobs * p.col_blocks * 1024);
+    p.part_col = take((size_t)kMaxColJobs * std::max(p.col_blocks, 256) * 1024);   // 256 >= CTAs of the tcgen05 grid
     p.part_gsq = take(p.gsq_blocks);
     if (p.nais)
       for (int l = 2; l <= p.L; ++l) {
@@ -183,11 +186,16 @@ static cudaEvent_t g_ev0[kMaxTimed], g_ev1[kMaxTimed];
 static double g_flops[kMaxTimed], g_bytes[kMaxTimed];
 static bool g_timed_tc[kMaxTimed];
 
+template <bool A_KC, bool B_KC>
+static bool uses_tc(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
+  return s->precision != FBSNN_PREC_FP32 && tc_eligible<A_KC, B_KC>(g, nsplit);
+}
+
 // dense layer dispatch: SIMT fp32, or tcgen05 TF32 when the variant is selected and the shape qualifies
 template <bool A_KC, bool B_KC, class Epi>
 static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nsplit, cudaStream_t st, const char* what,
                  bool allow_tc = true) {
-  const bool tc = allow_tc && s->precision == FBSNN_PREC_TF32 && tc_eligible<A_KC, B_KC>(g, nsplit);
+  const bool tc = allow_tc && s->precision != FBSNN_PREC_FP32 && tc_eligible<A_KC, B_KC>(g, nsplit);
   int slot = -1;
   if (g_timing && g_ntimed < kMaxTimed) {
     slot = g_ntimed++;
@@ -201,7 +209,10 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
     cudaEventRecord(g_ev0[slot], st);
   }
   ++g_launches;
-  cudaError_t e = tc ? launch_gemm_tc<A_KC, B_KC>(g, epi, nsplit, num_sms(), st) : launch_gemm<A_KC, B_KC>(g, epi, nsplit, num_sms(), st);
+  cudaError_t e;
+  if (!tc) e = launch_gemm<A_KC, B_KC>(g, epi, nsplit, num_sms(), st);
+  else if (s->precision == FBSNN_PREC_TF32X3) e = launch_gemm_tc<A_KC, B_KC, true>(g, epi, nsplit, num_sms(), st);
+  else e = launch_gemm_tc<A_KC, B_KC, false>(g, epi, nsplit, num_sms(), st);
   if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
   if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "%s gemm %s: %s", tc ? "tcgen05" : "simt", what, cudaGetErrorString(e));
   return 0;
@@ -274,8 +285,8 @@ static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* 
 static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, bool with_grad, cudaStream_t st) {
   const int R = (int)p.rows;
   int act = s->act_kind;
-  if (p.tf32 && act == FBSNN_ACT_SINE) act = kActSineFast;
-  if (p.tf32 && act == FBSNN_ACT_TANH) act = kActTanhFast;
+  if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_SINE) act = kActSineFast;
+  if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_TANH) act = kActTanhFast;
   for (int l = 1; l <= p.L; ++l) {
     GemmArgs g{};
     g.M = R, g.N = p.H[l], g.Nb = p.H[l], g.kchunk = 0;
@@ -290,7 +301,7 @@ static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float
         g.seg[1] = GemmSeg{ws + p.xin, n.Win[l], p.ldx, p.ldw, p.kin};
       }
     }
-    EpiFwd e{};
+    EpiFwdT<true> e{};
     e.bias1 = n.b[l], e.bias2 = n.bin[l];
     const bool res = p.nais && l >= 2;
     e.res = res ? ws + p.h[l - 1] : nullptr;
@@ -300,7 +311,7 @@ static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float
       e.wout = n.wout, e.delta = ws + p.delta[l], e.s = with_grad ? ws + p.szz[l] : nullptr;
     }
     e.ld = p.H[l], e.act = act;
-    int rc = dense<true, true>(s, g, e, 1, st, "F");
+    int rc = p.nais ? dense<true, true>(s, g, e, 1, st, "F") : dense<true, true>(s, g, narrow<EpiFwdT>(e), 1, st, "F");
     if (rc) return rc;
   }
   {
@@ -312,7 +323,7 @@ static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     GemmArgs g{};
     g.M = R, g.N = p.H[l - 1], g.Nb = p.H[l - 1], g.kchunk = 0, g.nseg = 1;
     g.seg[0] = GemmSeg{ws + p.delta[l], n.W[l], p.H[l], p.H[l - 1], p.H[l]};
-    EpiAdj e{};
+    EpiAdjT<true> e{};
     e.a = ws + p.a[l - 1], e.g = ws + p.g[l - 1];
     if (p.nais) {
       if (l == p.L) e.res_head = n.wout; else e.res = ws + p.ht[l];
@@ -321,7 +332,7 @@ static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     e.delta = ws + p.delta[l - 1];
     e.s = with_grad ? ws + p.szz[l - 1] : nullptr;
     e.ld = p.H[l - 1], e.act = act;
-    int rc = dense<true, false>(s, g, e, 1, st, "A");
+    int rc = p.nais ? dense<true, false>(s, g, e, 1, st, "A") : dense<true, false>(s, g, narrow<EpiAdjT>(e), 1, st, "A");
     if (rc) return rc;
   }
   {
@@ -370,6 +381,10 @@ static int wgrad(const FbsnnSpec* s, const Plan& p, float* ws, const float* P0, 
 
 static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, float* grads, cudaStream_t st) {
   const int R = (int)p.rows;
+  const int col_slots = std::max(p.col_blocks, 256);
+  auto col_part = [&](int job) { return ws + p.part_col + (size_t)job * col_slots * 1024; };   // job l = bias of layer l
+  bool fused_bias[kMaxL + 2] = {};
+  const int tc_grid = std::min<long long>(num_sms(), (p.rows + 127) / 128);
   // ---- T sweep -----------------------------------------------------------------------------------------
   for (int l = 1; l <= p.L; ++l) {
     GemmArgs g{};
@@ -385,13 +400,16 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
         g.seg[1] = GemmSeg{ws + p.V, n.Win[l], p.ldx, p.ldw, p.kin};
       }
     }
-    EpiTan e{};
+    EpiTanT<true> e{};
     e.a = ws + p.a[l], e.s_zz = ws + p.szz[l];
     e.res = (p.nais && l >= 2) ? ws + p.hd[l - 1] : nullptr;
     e.hd = ws + p.hd[l];
-    if (l == p.L) e.ybar = ws + p.ybar, e.wout = n.wout;
+    if (l == p.L) {
+      e.ybar = ws + p.ybar, e.wout = n.wout;
+      if (uses_tc<true, true>(s, g, 1)) e.colpart = col_part(l), fused_bias[l] = true;   // bias_L gradient fused
+    }
     e.ld = p.H[l];
-    int rc = dense<true, true>(s, g, e, 1, st, "T");
+    int rc = p.nais ? dense<true, true>(s, g, e, 1, st, "T") : dense<true, true>(s, g, narrow<EpiTanT>(e), 1, st, "T");
     if (rc) return rc;
   }
   // ---- B sweep -----------------------------------------------------------------------------------------
@@ -399,14 +417,15 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     GemmArgs g{};
     g.M = R, g.N = p.H[l - 1], g.Nb = p.H[l - 1], g.kchunk = 0, g.nseg = 1;
     g.seg[0] = GemmSeg{ws + p.szz[l], n.W[l], p.H[l], p.H[l - 1], p.H[l]};
-    EpiBwd e{};
+    EpiBwdT<true> e{};
     e.a = ws + p.a[l - 1], e.zz_zbar = ws + p.szz[l - 1];
     if (p.nais) {
       if (l == p.L) e.ybar = ws + p.ybar, e.wout = n.wout; else e.res = ws + p.hb[l];
       e.hb_out = (l - 1 >= 2) ? ws + p.hb[l - 1] : nullptr;
     }
     e.ld = p.H[l - 1];
-    int rc = dense<true, false>(s, g, e, 1, st, "B");
+    if (uses_tc<true, false>(s, g, 1)) e.colpart = col_part(l - 1), fused_bias[l - 1] = true;
+    int rc = p.nais ? dense<true, false>(s, g, e, 1, st, "B") : dense<true, false>(s, g, narrow<EpiBwdT>(e), 1, st, "B");
     if (rc) return rc;
   }
   // ---- G contractions ------------------------------------------------------------------------------------
@@ -438,13 +457,15 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
   }
   // ---- bias / output-layer gradients: column sums -----------------------------------------------------------
   ColJobs js{};
-  js.rows = p.rows, js.rows_per_block = p.col_rows_per_block, js.max_width = 1024, js.part = ws + p.part_col;
+  js.rows = p.rows, js.rows_per_block = p.col_rows_per_block, js.max_width = 1024;
   int maxw = 0;
   for (int l = 1; l <= p.L; ++l) {
     ColJob& j = js.job[js.njobs++];
-    j.A = ws + p.szz[l], j.B = nullptr, j.y = nullptr;
+    j.A = fused_bias[l] ? nullptr : ws + p.szz[l];
+    j.B = nullptr, j.y = nullptr;
     j.out = grads + s->off_b[l];
     j.out2 = (p.nais && l >= 2) ? grads + s->off_bin[l] : nullptr;
+    j.part = col_part(l), j.nblk = fused_bias[l] ? tc_grid : p.col_blocks;
     j.ld = p.H[l], j.width = p.H[l];
     maxw = std::max(maxw, p.H[l]);
   }
@@ -452,12 +473,13 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     ColJob& j = js.job[js.njobs++];
     j.A = ws + p.hd[p.L], j.B = ws + p.h[p.L], j.y = ws + p.ybar;
     j.out = grads + s->off_W[p.L + 1], j.out2 = nullptr;
+    j.part = col_part(0), j.nblk = p.col_blocks;
     j.ld = p.H[p.L], j.width = p.H[p.L];
   }
   if (maxw > 1024) return fail(FBSNN_E_UNSUPPORTED, "hidden width %d > 1024", maxw);
   colsum_stage1_kernel<<<dim3(p.col_blocks, js.njobs), 256, 0, st>>>(js);
   LAUNCH_CHECK("colsum1");
-  colsum_stage2_kernel<<<dim3((maxw + 255) / 256, js.njobs), 256, 0, st>>>(js, p.col_blocks);
+  colsum_stage2_kernel<<<dim3((maxw + 255) / 256, js.njobs), 256, 0, st>>>(js);
   LAUNCH_CHECK("colsum2");
   return 0;
 }
@@ -588,9 +610,15 @@ int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const 
   if (use_tc) {
     bool ok = a_kc && b_kc ? tc_eligible<true, true>(g, 1) : (a_kc ? tc_eligible<true, false>(g, 1) : tc_eligible<false, false>(g, 1));
     if (!ok || (!a_kc && b_kc)) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
-    if (a_kc && b_kc) err = launch_gemm_tc<true, true>(g, e, 1, num_sms(), st);
-    else if (a_kc) err = launch_gemm_tc<true, false>(g, e, 1, num_sms(), st);
-    else err = launch_gemm_tc<false, false>(g, e, 1, num_sms(), st);
+    if (use_tc == 2) {
+      if (a_kc && b_kc) err = launch_gemm_tc<true, true, true>(g, e, 1, num_sms(), st);
+      else if (a_kc) err = launch_gemm_tc<true, false, true>(g, e, 1, num_sms(), st);
+      else err = launch_gemm_tc<false, false, true>(g, e, 1, num_sms(), st);
+    } else {
+      if (a_kc && b_kc) err = launch_gemm_tc<true, true, false>(g, e, 1, num_sms(), st);
+      else if (a_kc) err = launch_gemm_tc<true, false, false>(g, e, 1, num_sms(), st);
+      else err = launch_gemm_tc<false, false, false>(g, e, 1, num_sms(), st);
+    }
   } else {
     if (a_kc && b_kc) err = launch_gemm<true, true>(g, e, 1, num_sms(), st);
     else if (a_kc) err = launch_gemm<true, false>(g, e, 1, num_sms(), st);

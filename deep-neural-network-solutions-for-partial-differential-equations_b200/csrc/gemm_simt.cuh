@@ -9,6 +9,8 @@
 // epilogue stores a partial tile; a deterministic second pass sums the partials (no atomics anywhere).
 // All output widths N and leading dimensions of epilogue arrays are multiples of 4 (float4 epilogue I/O).
 #pragma once
+#include <cstring>
+
 #include "common.cuh"
 
 namespace fbsnn {
@@ -32,15 +34,26 @@ struct GemmArgs {
 // Every epilogue is split in two so that the tcgen05 kernel can issue the loads of a whole 32-column chunk
 // before consuming them:  Frag f = prefetch(r, c)  reads the row-array inputs,  finish(r, c, acc, f)  computes
 // and stores.  operator() = finish(prefetch) for the SIMT kernel.
-struct Frag3 {
+// RES = the NAIS-Net residual-stream variant (one more row array in flight per element group); the FC variant
+// carries a smaller fragment so that the tcgen05 epilogue's 4-deep prefetch fits its register budget.
+template <bool RES>
+struct FragT {
   float4 x, y, z;
+};
+template <>
+struct FragT<false> {
+  float4 x, y;
 };
 #define FBSNN_EPI_CALL                                                                                   \
   __device__ __forceinline__ void operator()(int r, int c, float4 v) const { finish(r, c, v, prefetch(r, c)); }
 
 // F sweep: z = acc + bias;  g = act(z), a = act'(z);  h = g (+ h_prev);  last layer also seeds the adjoint
-struct EpiFwd {
-  typedef Frag3 Frag;
+template <bool RES>
+struct EpiFwdT {
+  struct Frag {
+    float4 y;   // h_{l-1} (RES only)
+  };
+  static constexpr bool kColsum = false;
   const float* bias1;
   const float* bias2;  // nullable (NAIS: layer{l}_input.bias)
   const float* res;    // nullable: h_{l-1} (NAIS residual stream)
@@ -55,26 +68,26 @@ struct EpiFwd {
   int io_arrays() const { return 2 + (h ? 2 : 0) + (wout ? (s ? 2 : 1) : 0); }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     Frag f;
-    f.x = ld4(bias1 + c);
-    if (bias2) {
-      const float4 b2 = ld4(bias2 + c);
-      f.x.x += b2.x, f.x.y += b2.y, f.x.z += b2.z, f.x.w += b2.w;
-    }
-    f.y = h ? ld4(res + (size_t)r * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    f.z = wout ? ld4(wout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (RES && h) f.y = ld4(res + (size_t)r * ld + c);
+    else f.y = make_float4(0.f, 0.f, 0.f, 0.f);
     return f;
   }
   __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
-    const float z[4] = {v.x + f.x.x, v.y + f.x.y, v.z + f.x.z, v.w + f.x.w};
+    float4 b = ld4(bias1 + c);   // small, L1-resident
+    if (bias2) {
+      const float4 b2 = ld4(bias2 + c);
+      b.x += b2.x, b.y += b2.y, b.z += b2.z, b.w += b2.w;
+    }
+    const float z[4] = {v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w};
     float gv[4], av[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) act_ga(act, z[i], gv[i], av[i]);
     const size_t o = (size_t)r * ld + c;
     st4(g + o, make_float4(gv[0], gv[1], gv[2], gv[3]));
     st4(a + o, make_float4(av[0], av[1], av[2], av[3]));
-    if (h) st4(h + o, make_float4(gv[0] + f.y.x, gv[1] + f.y.y, gv[2] + f.y.z, gv[3] + f.y.w));
+    if (RES && h) st4(h + o, make_float4(gv[0] + f.y.x, gv[1] + f.y.y, gv[2] + f.y.z, gv[3] + f.y.w));
     if (wout) {
-      const float4 w = f.z;
+      const float4 w = ld4(wout + c);
       st4(delta + o, make_float4(w.x * av[0], w.y * av[1], w.z * av[2], w.w * av[3]));
       if (s)
         st4(s + o, make_float4(w.x * act_c(act, gv[0], av[0]), w.y * act_c(act, gv[1], av[1]),
@@ -85,8 +98,10 @@ struct EpiFwd {
 };
 
 // A sweep (writes layer l-1): ht = acc (+ ht_l | + wout);  delta = ht * a;  s = ht * c
-struct EpiAdj {
-  typedef Frag3 Frag;
+template <bool RES>
+struct EpiAdjT {
+  typedef FragT<RES> Frag;
+  static constexpr bool kColsum = false;
   const float* a;
   const float* g;
   const float* res;       // nullable: ht_l (NAIS)
@@ -101,31 +116,35 @@ struct EpiAdj {
     Frag f;
     f.x = ld4(a + o);
     f.y = s ? ld4(g + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-    f.z = res ? ld4(res + o) : (res_head ? ld4(res_head + c) : make_float4(0.f, 0.f, 0.f, 0.f));
+    if constexpr (RES) f.z = res ? ld4(res + o) : (res_head ? ld4(res_head + c) : make_float4(0.f, 0.f, 0.f, 0.f));
     return f;
   }
   __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
     const size_t o = (size_t)r * ld + c;
-    const float ht[4] = {v.x + f.z.x, v.y + f.z.y, v.z + f.z.z, v.w + f.z.w};
+    float ht[4] = {v.x, v.y, v.z, v.w};
+    if constexpr (RES) ht[0] += f.z.x, ht[1] += f.z.y, ht[2] += f.z.z, ht[3] += f.z.w;
     const float4 av = f.x, gv = f.y;
     st4(delta + o, make_float4(ht[0] * av.x, ht[1] * av.y, ht[2] * av.z, ht[3] * av.w));
     if (s)
       st4(s + o, make_float4(ht[0] * act_c(act, gv.x, av.x), ht[1] * act_c(act, gv.y, av.y),
                              ht[2] * act_c(act, gv.z, av.z), ht[3] * act_c(act, gv.w, av.w)));
-    if (ht_out) st4(ht_out + o, make_float4(ht[0], ht[1], ht[2], ht[3]));
+    if (RES && ht_out) st4(ht_out + o, make_float4(ht[0], ht[1], ht[2], ht[3]));
   }
   FBSNN_EPI_CALL
 };
 
 // T sweep (layer l): dbar = acc;  hd = dbar * a (+ hd_{l-1});  zz = dbar * s;  last layer: zbar = ybar*wout*a + zz
-struct EpiTan {
-  typedef Frag3 Frag;
+template <bool RES>
+struct EpiTanT {
+  typedef FragT<RES> Frag;
+  static constexpr bool kColsum = true;
   const float* a;
   float* s_zz;        // in: s, out: zz (or zbar for the last layer)
   const float* res;   // nullable: hd_{l-1}
   float* hd;
   const float* ybar;  // nullable: last layer
   const float* wout;
+  float* colpart;     // nullable: [grid][1024] per-CTA column sums of zbar (last layer), tcgen05 kernel only
   int ld;
   int io_arrays() const { return 4 + (res ? 1 : 0); }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
@@ -133,13 +152,14 @@ struct EpiTan {
     Frag f;
     f.x = ld4(a + o);
     f.y = ld4(s_zz + o);
-    f.z = res ? ld4(res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (RES) f.z = res ? ld4(res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
     return f;
   }
-  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
+  __device__ __forceinline__ float4 finish(int r, int c, float4 v, const Frag& f) const {
     const size_t o = (size_t)r * ld + c;
     const float4 av = f.x, sv = f.y;
-    const float hdv[4] = {v.x * av.x + f.z.x, v.y * av.y + f.z.y, v.z * av.z + f.z.z, v.w * av.w + f.z.w};
+    float hdv[4] = {v.x * av.x, v.y * av.y, v.z * av.z, v.w * av.w};
+    if constexpr (RES) hdv[0] += f.z.x, hdv[1] += f.z.y, hdv[2] += f.z.z, hdv[3] += f.z.w;
     float zz[4] = {v.x * sv.x, v.y * sv.y, v.z * sv.z, v.w * sv.w};
     if (wout) {
       const float yb = ybar[r];
@@ -148,19 +168,23 @@ struct EpiTan {
     }
     st4(hd + o, make_float4(hdv[0], hdv[1], hdv[2], hdv[3]));
     st4(s_zz + o, make_float4(zz[0], zz[1], zz[2], zz[3]));
+    return make_float4(zz[0], zz[1], zz[2], zz[3]);
   }
   FBSNN_EPI_CALL
 };
 
 // B sweep (writes layer l-1): hb = acc (+ hb_l | + ybar*wout);  zbar = hb * a + zz
-struct EpiBwd {
-  typedef Frag3 Frag;
+template <bool RES>
+struct EpiBwdT {
+  typedef FragT<RES> Frag;
+  static constexpr bool kColsum = true;
   const float* a;
   float* zz_zbar;
   const float* res;   // nullable: hb_l (NAIS, l < L)
   const float* ybar;  // nullable: NAIS l = L, residual is ybar[r] * wout[c]
   const float* wout;
   float* hb_out;      // nullable
+  float* colpart;     // nullable: [grid][1024] per-CTA column sums of zbar, tcgen05 kernel only
   int ld;
   int io_arrays() const { return 3 + (res ? 1 : 0) + (hb_out ? 1 : 0); }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
@@ -168,30 +192,45 @@ struct EpiBwd {
     Frag f;
     f.x = ld4(a + o);
     f.y = ld4(zz_zbar + o);
-    if (res) {
-      f.z = ld4(res + o);
-    } else if (ybar) {
-      const float yb = ybar[r];
-      const float4 w = ld4(wout + c);
-      f.z = make_float4(yb * w.x, yb * w.y, yb * w.z, yb * w.w);
-    } else {
-      f.z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (RES) {
+      if (res) {
+        f.z = ld4(res + o);
+      } else if (ybar) {
+        const float yb = ybar[r];
+        const float4 w = ld4(wout + c);
+        f.z = make_float4(yb * w.x, yb * w.y, yb * w.z, yb * w.w);
+      } else {
+        f.z = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     return f;
   }
-  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
+  __device__ __forceinline__ float4 finish(int r, int c, float4 v, const Frag& f) const {
     const size_t o = (size_t)r * ld + c;
-    const float hb[4] = {v.x + f.z.x, v.y + f.z.y, v.z + f.z.z, v.w + f.z.w};
+    float hb[4] = {v.x, v.y, v.z, v.w};
+    if constexpr (RES) hb[0] += f.z.x, hb[1] += f.z.y, hb[2] += f.z.z, hb[3] += f.z.w;
     const float4 av = f.x, zz = f.y;
-    st4(zz_zbar + o, make_float4(hb[0] * av.x + zz.x, hb[1] * av.y + zz.y, hb[2] * av.z + zz.z, hb[3] * av.w + zz.w));
-    if (hb_out) st4(hb_out + o, make_float4(hb[0], hb[1], hb[2], hb[3]));
+    const float4 zb = make_float4(hb[0] * av.x + zz.x, hb[1] * av.y + zz.y, hb[2] * av.z + zz.z, hb[3] * av.w + zz.w);
+    st4(zz_zbar + o, zb);
+    if (RES && hb_out) st4(hb_out + o, make_float4(hb[0], hb[1], hb[2], hb[3]));
+    return zb;
   }
   FBSNN_EPI_CALL
 };
 
+// same members in both variants: the FC form is obtained by reinterpreting the filled-in NAIS form
+template <template <bool> class E>
+inline E<false> narrow(const E<true>& e) {
+  static_assert(sizeof(E<false>) == sizeof(E<true>), "epilogue variants must share their layout");
+  E<false> r;
+  memcpy(&r, &e, sizeof(r));
+  return r;
+}
+
 struct FragNone {};
 struct EpiStore {
   typedef FragNone Frag;
+  static constexpr bool kColsum = false;
   float* out;
   int ld;
   int io_arrays() const { return 1; }
@@ -203,6 +242,7 @@ struct EpiStore {
 // split-K partial tile: out[z][M][N]; `z` is blockIdx.z in the SIMT kernel, the split index in the tcgen05 kernel
 struct EpiPartial {
   typedef FragNone Frag;
+  static constexpr bool kColsum = false;
   float* out;
   int M, N;
   int io_arrays() const { return 1; }

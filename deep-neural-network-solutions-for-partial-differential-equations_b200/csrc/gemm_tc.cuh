@@ -4,7 +4,7 @@
 // for shapes that are genuine dense GEMMs:  N in {64,128,192,256}, every K a multiple of 32 (sweeps), leading
 // dimensions multiples of 4 floats.  Everything else stays on the SIMT kernel.
 //
-// CTA = 10 warps, persistent (one CTA per SM, static round-robin over 128-row output tiles):
+// CTA = 10 warps (14 with SPLIT3), persistent (one CTA per SM, static round-robin over 128-row output tiles):
 //   warp 0     TMA producer: cp.async.bulk.tensor 128B-swizzled boxes into a 4-stage ring (48 KB per stage)
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32, M=128, N<=256, K=8;
 //              owns the 512-column TMEM allocation = two accumulator buffers (epilogue of tile i overlaps MMA of i+1)
@@ -26,15 +26,11 @@
 namespace fbsnn {
 namespace tc {
 
-constexpr int BM = 128, BK = 32, STAGES = 3, UMMA_K = 8;
+constexpr int BM = 128, BK = 32, UMMA_K = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 4;       // 16 KB
 constexpr int B_STAGE_BYTES = 256 * BK * 4;      // 32 KB (N <= 256)
-constexpr int NUM_THREADS = 320;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int EPI_LD = 36;                                      // padded row of the per-warp 32x32 transpose tile
-constexpr int EPI_TILE_BYTES = 32 * EPI_LD * 4;                 // 4.5 KB per epilogue warp
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_EPI_WARPS * EPI_TILE_BYTES +
-                           1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_TILE_BYTES = 32 * 32 * 4;      // per-warp 32x32 fp32 transpose tile (XOR-swizzled, no padding)
 constexpr uint32_t kSpinLimit = 1u << 24;       // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct TmSet {
@@ -120,20 +116,37 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b
       : "r"(taddr))
 
 // ----------------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// SPLIT3 = fp32-grade accuracy on the tensor cores ("3xTF32"): every operand tile x is used as hi = trunc_tf32(x)
+// (what the UMMA reads from the fp32 container anyway) and lo = x - hi, written by four splitter warps into a second
+// pair of smem tiles as soon as the TMA lands; three MMAs per k-step accumulate lo*hi + hi*lo + hi*hi in TMEM.
+// The dropped lo*lo term and the truncation of lo are ~2^-21 relative.  The kernel stays HBM-bound (the tensor
+// pipe was 13-39 % busy with one MMA per k-step), so this costs little time; it costs shared memory: 2 stages.
+template <bool SPLIT3>
+struct Cfg {
+  static constexpr int STAGES = SPLIT3 ? 2 : 3;
+  static constexpr int SPLIT_WARPS = SPLIT3 ? 4 : 0;
+  static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
+  static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
+  static constexpr int STAGE_BYTES = (A_STAGE_BYTES + B_STAGE_BYTES) * (SPLIT3 ? 2 : 1);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES + 1024 /*align*/ + 256;
+};
+
+template <bool A_MN, bool B_MN, bool SPLIT3, class Epi>
+__global__ void __launch_bounds__(Cfg<SPLIT3>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi, const int num_mtiles, const int nsplit) {
+  using C = Cfg<SPLIT3>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  float* epi_tiles = (float*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_EPI_WARPS * EPI_TILE_BYTES);
-  uint64_t* full = bars;               // [STAGES]
-  uint64_t* empty = bars + STAGES;     // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES; // [2]
-  uint64_t* tempty = tfull + 2;        // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  // stage layout: [A 16K][B 32K]([A_lo 16K][B_lo 32K])
+  float* epi_tiles = (float*)(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES);
+  uint64_t* full = bars;               // [STAGES]  TMA bytes landed
+  uint64_t* empty = bars + 3;          // [STAGES]  MMAs that read the stage have completed
+  uint64_t* sdone = bars + 6;          // [STAGES]  lo tiles written (SPLIT3)
+  uint64_t* tfull = bars + 9;          // [2]       accumulator complete
+  uint64_t* tempty = bars + 11;        // [2]       accumulator drained by the epilogue
+  uint32_t* tmem_slot = (uint32_t*)(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = g.N;
@@ -144,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.a[s]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b[s]) : "memory");
     }
-    for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1), mbar_init(&sdone[i], 4);
     for (int i = 0; i < 2; ++i) mbar_init(&tfull[i], 1), mbar_init(&tempty[i], NUM_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -175,8 +188,8 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
           for (int k0 = kbeg(s, split), ke = kend(s, split); k0 < ke; k0 += BK) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_expect_tx(&full[stage], bytes);
-            uint8_t* a = sA + stage * A_STAGE_BYTES;
-            uint8_t* b = sB + stage * B_STAGE_BYTES;
+            uint8_t* a = smem + stage * C::STAGE_BYTES;
+            uint8_t* b = a + A_STAGE_BYTES;
             if (A_MN) {
 #pragma unroll
               for (int c = 0; c < BM / 32; ++c) tma_load_2d(a + c * 4096, &tm.a[s], &full[stage], m0 + 32 * c, k0);
@@ -207,15 +220,22 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
         uint32_t first = 1;
         for (int s = 0; s < g.nseg; ++s) {
           for (int k0 = kbeg(s, split), ke = kend(s, split); k0 < ke; k0 += BK) {
-            mbar_wait(&full[stage], phase);
+            mbar_wait(SPLIT3 ? &sdone[stage] : &full[stage], phase);
             tc_fence_after();
-            const uint32_t a = smem_u32(sA + stage * A_STAGE_BYTES);
-            const uint32_t b = smem_u32(sB + stage * B_STAGE_BYTES);
+            const uint32_t a = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint32_t b = a + A_STAGE_BYTES;
+            const uint32_t alo = a + A_STAGE_BYTES + B_STAGE_BYTES, blo = alo + A_STAGE_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adesc = A_MN ? make_desc(a + k * 1024, 4096, 512, 1) : make_desc(a + k * 32, 16, 1024, 2);
-              const uint64_t bdesc = B_MN ? make_desc(b + k * 1024, 4096, 512, 1) : make_desc(b + k * 32, 16, 1024, 2);
-              umma_tf32(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+              auto da = [&](uint32_t base) { return A_MN ? make_desc(base + k * 1024, 4096, 512, 1) : make_desc(base + k * 32, 16, 1024, 2); };
+              auto db = [&](uint32_t base) { return B_MN ? make_desc(base + k * 1024, 4096, 512, 1) : make_desc(base + k * 32, 16, 1024, 2); };
+              if (SPLIT3) {
+                umma_tf32(tmem_d, da(alo), db(b), idesc, first ? 0u : 1u);
+                umma_tf32(tmem_d, da(a), db(blo), idesc, 1u);
+                umma_tf32(tmem_d, da(a), db(b), idesc, 1u);
+              } else {
+                umma_tf32(tmem_d, da(a), db(b), idesc, first ? 0u : 1u);
+              }
               first = 0;
             }
             umma_commit(&empty[stage]);   // smem slot free once these MMAs have read it
@@ -225,16 +245,60 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
         umma_commit(&tfull[acc]);         // accumulator complete
       }
     }
+  } else if (SPLIT3 && warp < C::EPI_WARP0) {
+    // ===================== splitter warps (SPLIT3): lo = x - trunc_tf32(x) for both operand tiles ==============
+    const int ts = threadIdx.x - 64;
+    const int nA4 = A_STAGE_BYTES / 16, nB4 = N * BK * 4 / 16;
+    uint32_t stage = 0, phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int split = w / num_mtiles;
+      for (int s = 0; s < g.nseg; ++s) {
+        for (int k0 = kbeg(s, split), ke = kend(s, split); k0 < ke; k0 += BK) {
+          mbar_wait(&full[stage], phase);
+          const float4* a = (const float4*)(smem + stage * C::STAGE_BYTES);
+          float4* lo = (float4*)(smem + stage * C::STAGE_BYTES + A_STAGE_BYTES + B_STAGE_BYTES);
+          // A tile [0, nA4) maps to lo[0, nA4); B tile starts at A_STAGE_BYTES in both halves
+          // A and B tiles are contiguous ([A 16K][B N*128]) in both halves of the stage: one flat loop, 8 loads in
+          // flight per thread
+          const int n4 = nA4 + nB4;
+          for (int i0 = ts; i0 < n4; i0 += 128 * 8) {
+            float4 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i0 + u * 128 < n4) x[u] = a[i0 + u * 128];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i0 + u * 128 < n4) {
+                float4 l;
+                l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
+                l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
+                l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
+                l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
+                lo[i0 + u * 128] = l;
+              }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sdone[stage]);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
   } else {
     // ===================== epilogue warps =====================
     // TMEM hands each lane one accumulator ROW; the row arrays in global memory want a warp on one row's
-    // contiguous columns.  Each 32x32 chunk is therefore transposed through a warp-private padded smem tile, after
-    // which 8 lanes cover 128 B of one row and a warp-wide access touches 4 full cache lines instead of 32 partial.
+    // contiguous columns.  Each 32x32 chunk is therefore transposed through a warp-private XOR-swizzled smem tile,
+    // after which 8 lanes cover 128 B of one row and a warp-wide access touches 4 full cache lines instead of 32.
+    const int e = warp - C::EPI_WARP0;
     const int q = warp & 3;                // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;      // column half
+    const int half = e >> 2;               // column half
     const int ncol = N >> 1;
-    float* tile = epi_tiles + (warp - 2) * (32 * EPI_LD);
-    const int sub = lane >> 3, cc = (lane & 7) * 4;
+    float* tile = epi_tiles + e * (EPI_TILE_BYTES / 4);
+    const int sub = lane >> 3, c4 = lane & 7;
+    constexpr bool kColsum = Epi::kColsum;
+    float4 csum[4];                        // per-thread column sums of zbar: chunk x 4 columns (N/2 <= 128)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) csum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int mt = w % num_mtiles;
@@ -244,40 +308,84 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
       const int r0 = mt * BM + q * 32;
-      for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 32) {
+#pragma unroll 1
+      for (int ch = 0; ch * 32 < ncol; ++ch) {
+        const int c0 = half * ncol + ch * 32;
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c0;
         FBSNN_TMEM_LD32(taddr, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          st4(tile + lane * EPI_LD + 4 * j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+          st4(tile + lane * 32 + ((j ^ (lane & 7)) << 2),
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3])));
         __syncwarp();
+        const int cc = c4 * 4;
 #pragma unroll
         for (int ib = 0; ib < 2; ++ib) {
           typename Epi::Frag f[4];
-          float4 a4[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = (ib * 4 + i) * 4 + sub;
             if (r0 + rr < g.M) f[i] = epi.prefetch(r0 + rr, c0 + cc);
-            a4[i] = ld4(tile + rr * EPI_LD + cc);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = (ib * 4 + i) * 4 + sub;
+            const float4 a4 = ld4(tile + rr * 32 + ((c4 ^ (rr & 7)) << 2));
             if (r0 + rr < g.M) {
-              if constexpr (std::is_same<Epi, EpiPartial>::value) epi.finish_split(split, r0 + rr, c0 + cc, a4[i]);
-              else epi.finish(r0 + rr, c0 + cc, a4[i], f[i]);
+              if constexpr (std::is_same<Epi, EpiPartial>::value) {
+                epi.finish_split(split, r0 + rr, c0 + cc, a4);
+              } else if constexpr (kColsum) {
+                const float4 zb = epi.finish(r0 + rr, c0 + cc, a4, f[i]);
+                cs.x += zb.x, cs.y += zb.y, cs.z += zb.z, cs.w += zb.w;
+              } else {
+                epi.finish(r0 + rr, c0 + cc, a4, f[i]);
+              }
             }
           }
         }
         __syncwarp();
+        if constexpr (kColsum) {   // rolled loop: select the chunk's accumulator with predicated adds (no local memory)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (ch == k) csum[k].x += cs.x, csum[k].y += cs.y, csum[k].z += cs.z, csum[k].w += cs.w;
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if constexpr (kColsum) {
+      // fused bias gradient: per-CTA column sums of zbar -> colpart[blockIdx.x][col]; fixed reduction order
+      // (4 row groups of a warp by shuffle, then the 4 lane-quarter warps of a column half through smem).
+      if (epi.colpart) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float4 t = csum[ch];
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            t.x += __shfl_xor_sync(0xffffffffu, t.x, o), t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+            t.z += __shfl_xor_sync(0xffffffffu, t.z, o), t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+          }
+          if (sub == 0 && ch * 32 < ncol) st4(tile + ch * 32 + c4 * 4, t);   // this warp's 32 x ncol/32 sums
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");                       // the 8 epilogue warps only
+        if (q == 0) {
+          for (int c = lane; c < ncol; c += 32) {
+            float tot = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              // warp with lane-quarter qq and this column half: e' such that (EPI_WARP0 + e') & 3 == qq, e' >> 2 == half
+              const int e2 = half * 4 + ((qq - C::EPI_WARP0) & 3);
+              tot += epi_tiles[e2 * (EPI_TILE_BYTES / 4) + c];
+            }
+            epi.colpart[(size_t)blockIdx.x * 1024 + half * ncol + c] = tot;
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -336,9 +444,10 @@ inline bool tc_eligible(const GemmArgs& g, int nsplit) {
   return true;
 }
 
-template <bool A_KC, bool B_KC, class Epi>
+template <bool A_KC, bool B_KC, bool SPLIT3, class Epi>
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
   constexpr bool A_MN = !A_KC, B_MN = !B_KC;
+  using C = tc::Cfg<SPLIT3>;
   tc::TmSet tm;
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
@@ -350,17 +459,17 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit,
     if (!ok) return cudaErrorInvalidValue;
   }
   for (int s = g.nseg; s < 4; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];
-  auto kern = tc::gemm_tc_kernel<A_MN, B_MN, Epi>;
+  auto kern = tc::gemm_tc_kernel<A_MN, B_MN, SPLIT3, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int mtiles = (g.M + tc::BM - 1) / tc::BM;
   const int work = mtiles * nsplit;
   const int grid = work < num_sms ? work : num_sms;
-  kern<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(tm, g, epi, mtiles, nsplit);
+  kern<<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(tm, g, epi, mtiles, nsplit);
   return cudaGetLastError();
 }
 

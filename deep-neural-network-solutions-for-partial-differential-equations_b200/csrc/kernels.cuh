@@ -308,11 +308,13 @@ __global__ void final_sum2_kernel(const float* __restrict__ part, int n, FinalSu
 //   job j: out[c] = sum_r ( A[r*ld + c] + (B ? y[r] * B[r*ld + c] : 0) )
 // ----------------------------------------------------------------------------------------------------
 struct ColJob {
-  const float* A;
+  const float* A;   // null: the per-CTA partials were already written by the tcgen05 sweep epilogue (fused)
   const float* B;   // nullable
   const float* y;   // with B
   float* out;       // final destination(s)
   float* out2;      // nullable second destination (NAIS: layer{l}.bias and layer{l}_input.bias share a gradient)
+  float* part;      // [nblk][max_width] partial sums of this job
+  int nblk;
   int ld, width;
 };
 constexpr int kMaxColJobs = 12;
@@ -322,11 +324,11 @@ struct ColJobs {
   long long rows;
   int rows_per_block;
   int max_width;
-  float* part;  // [njobs][gridDim.x][max_width]
 };
 
 __global__ void colsum_stage1_kernel(const ColJobs js) {
   const ColJob& j = js.job[blockIdx.y];
+  if (!j.A) return;
   const long long r0 = (long long)blockIdx.x * js.rows_per_block;
   const long long r1 = min(js.rows, r0 + js.rows_per_block);
   for (int c = threadIdx.x; c < j.width; c += blockDim.x) {
@@ -336,15 +338,15 @@ __global__ void colsum_stage1_kernel(const ColJobs js) {
     } else {
       for (long long r = r0; r < r1; ++r) acc += j.A[r * j.ld + c];
     }
-    js.part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * js.max_width + c] = acc;
+    j.part[(size_t)blockIdx.x * js.max_width + c] = acc;
   }
 }
-__global__ void colsum_stage2_kernel(const ColJobs js, int nblk) {
+__global__ void colsum_stage2_kernel(const ColJobs js) {
   const ColJob& j = js.job[blockIdx.y];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= j.width) return;
   float acc = 0.f;
-  for (int b = 0; b < nblk; ++b) acc += js.part[((size_t)blockIdx.y * nblk + b) * js.max_width + c];
+  for (int b = 0; b < j.nblk; ++b) acc += j.part[(size_t)b * js.max_width + c];
   j.out[c] = acc;
   if (j.out2) j.out2[c] = acc;
 }

@@ -13,7 +13,7 @@ MU_ZERO, MU_LINEAR = 0, 1
 SIGMA_CONST, SIGMA_PROP = 0, 1
 PHI_BSB, PHI_RY, PHI_ZSQ = 0, 1, 2
 G_SUMSQ, G_CALL_SUM, G_CALL_MEAN, G_LOGQ = 0, 1, 2, 3
-PRECISION = {"fp32": 0, "tf32": 1}
+PRECISION = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 
 class FbsnnSpec(C.Structure):

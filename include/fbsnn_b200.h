@@ -35,7 +35,8 @@ enum { FBSNN_PHI_BSB = 0, FBSNN_PHI_RY = 1, FBSNN_PHI_ZSQ = 2 }; /* c(Y - X.Z) |
 enum { FBSNN_G_SUMSQ = 0, FBSNN_G_CALL_SUM = 1, FBSNN_G_CALL_MEAN = 2, FBSNN_G_LOGQ = 3 };
 /* arithmetic variant of the dense layers */
 enum { FBSNN_PREC_FP32 = 0,      /* SIMT fp32 FMA: parity-grade (tolerances in tests/test_parity_gpu.py)     */
-       FBSNN_PREC_TF32 = 1 };    /* tcgen05 kind::tf32, fp32 accumulate in TMEM: large-M throughput variant  */
+       FBSNN_PREC_TF32 = 1,      /* tcgen05 kind::tf32, fp32 accumulate in TMEM: large-M throughput variant  */
+       FBSNN_PREC_TF32X3 = 2 };  /* tcgen05, operands split hi+lo in smem, 3 MMAs per k-step: fp32-grade     */
 
 typedef struct FbsnnSpec {
   int32_t D;                          /* state dimension                                                      */
@@ -72,7 +73,8 @@ long long fbsnn_launch_count(void);
 void fbsnn_dense_timing(int enable);
 int fbsnn_dense_timing_read(double* out8);
 
-/* Test hook (tests/test_gemm_gpu.py): one dense GEMM with a plain store on the SIMT (use_tc = 0) or tcgen05 kernel.
+/* Test hook (tests/test_gemm_gpu.py): one dense GEMM with a plain store on the SIMT (use_tc = 0), tcgen05 TF32
+ * (use_tc = 1) or tcgen05 3xTF32 (use_tc = 2) kernel.
  * a_kc: A[m*lda + k] (1) | A[k*lda + m] (0);  b_kc: B[n*ldb + k] (1) | B[k*ldb + n] (0);  C[m*ldc + n]. */
 int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const float* A, int lda, const float* B,
                      int ldb, float* C, int ldc, void* stream);

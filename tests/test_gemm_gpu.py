@@ -51,3 +51,15 @@ def test_tcgen05_gemm(a_kc, b_kc, M, N, K):
     assert (err <= 2e-3 * bound + 1e-5).all(), float((err / (bound + 1e-9)).max())
     # and it is genuinely TF32 arithmetic, not fp32 (guards against a silent SIMT dispatch)
     assert float(err.max()) > 1e-6
+
+
+@pytest.mark.parametrize("a_kc,b_kc", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (300, 256, 256), (5100, 128, 256), (40000, 256, 128)])
+def test_tcgen05_3xtf32_gemm_is_fp32_grade(a_kc, b_kc, M, N, K):
+    """operands split hi + lo in shared memory, three MMAs per k-step: error ~2^-21 of sum|a||b|, i.e. fp32-grade."""
+    if not a_kc:
+        M, K = (256 if M % 128 else M), max(K, 1000 if K == 256 else K)
+    C, ref, bound = run_gemm(a_kc, b_kc, 2, M, N, K)
+    assert torch.isfinite(C).all()
+    err = (C.double() - ref).abs()
+    assert (err <= 2e-6 * bound + 1e-6).all(), float((err / (bound + 1e-9)).max())

@@ -133,3 +133,26 @@ def test_tf32_variant_runs_on_tensor_cores():
     assert lib.fbsnn_dense_timing_read(out) == 0
     lib.fbsnn_dense_timing(0)
     assert out[0] == 19 and out[3] == 19, list(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3xTF32 tensor-core variant (precision="tf32x3"): same tcgen05 kernel, operands split hi + lo, fp32-grade products.
+# Held to the fp32 tolerances above except where the truncating split (bias ~2^-21 per product) shows: x5.
+TOL_X3 = {k: v * 5 for k, v in TOL.items()}
+TOL_X3["X_abs"] = 1e-6
+
+
+@pytest.mark.parametrize("name", gu.solver_cases())
+def test_tf32x3_variant_is_fp32_grade(name):
+    from tests import parity_util as pu
+    g, meta = gu.load(name)
+    sol, oracle = pu.build_cuda_solver(meta, g, precision="tf32x3")
+    errs = pu.single_eval_errors(sol, oracle, g, meta)
+    for k, v in errs.items():
+        if k in TOL_X3:
+            assert v <= TOL_X3[k], (name, k, v, errs)
+    if meta["D"] == 1 and meta["M"] > 1:
+        return
+    terr = pu.train_trace_errors(sol, g, meta)
+    for k, v in terr.items():
+        assert v <= TOL_X3[k], (name, k, v, terr)

@@ -190,6 +190,26 @@ class FBSNN(ABC):
         W = torch.from_numpy(np.cumsum(DW, axis=1)).float().to(self.device)
         return t, W
 
+    def fetch_minibatch_device(self, seed=None, iteration=0, path_offset=0, n_paths=None):
+        """Device-side twin of fetch_minibatch(): same layout and distribution (incl. the Cholesky-correlated form),
+        drawn by Philox4x32-10 keyed (seed, iteration, GLOBAL path id) -- so any contiguous shard
+        [path_offset, path_offset + n_paths) reproduces exactly the rows of the full minibatch.  Not NumPy's
+        stream."""
+        lib = self._require_cuda()
+        M = self.M if n_paths is None else int(n_paths)
+        sp = self._spec()
+        dev = self.device
+        with torch.cuda.device(dev):
+            ws = self._workspace(lib, sp, M, True)
+            t = torch.empty(M, self.N + 1, 1, device=dev)
+            W = torch.empty(M, self.N + 1, self.D, device=dev)
+            chol = self._chol_device()
+            rc = lib.fbsnn_fetch_minibatch(ctypes.byref(sp), float(self.T), M, int(path_offset),
+                                           int(self.seed if seed is None else seed), int(iteration), _ptr(chol),
+                                           _ptr(ws), ws.numel(), _ptr(t), _ptr(W), self._stream())
+            _lib.check(rc, "fbsnn_fetch_minibatch")
+        return t, W
+
     # ------------------------------------------------------------------------------------------------
     # kernel plumbing
     # ------------------------------------------------------------------------------------------------

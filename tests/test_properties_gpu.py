@@ -1,0 +1,182 @@
+"""Size-independent properties of the CUDA path at sizes the CPU oracle cannot reach, edge cases, and the
+Monte-Carlo pricer (statistical parity with the reference algorithm, known answers, sharding invariance)."""
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+D, N = 100, 50
+LAYERS = [D + 1] + 4 * [256] + [1]
+
+
+def _bsb(M, precision="fp32", **kw):
+    import dnnpde_b200 as pde
+    torch.manual_seed(11)
+    return pde.BlackScholesBarenblatt(gu.make_xi("bsb", D), 1.0, M, N, D, LAYERS, "FC", "Sine", precision=precision,
+                                      seed=5, **kw)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_loss_and_gradient_are_additive_over_path_shards(precision):
+    """loss and d(loss)/d(theta) are sums over paths: full batch == sum of shards (what multi-GPU sharding uses)."""
+    M = 8192
+    sol = _bsb(M, precision)
+    t, W = sol.fetch_minibatch_device(iteration=3)
+    loss, X, Y, _, g = sol.loss_grad_flat(t, W)
+    loss, g, Y = float(loss), g.clone(), Y.clone()
+    acc_l, acc_g = 0.0, torch.zeros_like(g)
+    for lo, hi in ((0, 3000), (3000, 8192)):
+        sol.M = hi - lo
+        l, _, Ys, _, gs = sol.loss_grad_flat(t[lo:hi].contiguous(), W[lo:hi].contiguous())
+        acc_l += float(l)
+        acc_g += gs
+        assert torch.equal(Ys, Y[lo:hi])                       # per-row results do not depend on the batch
+    assert abs(acc_l - loss) <= 2e-6 * abs(loss)
+    assert float((acc_g - g).abs().max()) <= 2e-5 * float(g.abs().max())
+    # all paths start at Xi => one Y0, one Z0
+    assert float(Y[:, 0, 0].max() - Y[:, 0, 0].min()) == 0.0
+
+
+def test_path_advance_matches_fp64_recursion_at_full_size():
+    M = 65536
+    sol = _bsb(M)
+    t, W = sol.fetch_minibatch_device(iteration=1)
+    X, Y = sol.predict(gu.make_xi("bsb", D), t, W)
+    dW = (W[:, 1:] - W[:, :-1]).double()
+    ref = torch.cumprod(torch.cat((torch.ones(M, 1, D, device=W.device, dtype=torch.float64), 1 + 0.4 * dW), 1), 1)
+    ref = ref * torch.as_tensor(gu.make_xi("bsb", D), device=W.device)
+    assert float((X.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    assert torch.isfinite(Y).all() and Y.shape == (M, N + 1, 1)
+
+
+def test_device_brownian_statistics_and_shard_invariance():
+    import dnnpde_b200 as pde
+    np.random.seed(2)
+    sol = pde.BasketCallOption(np.ones((1, 20)), 1.0, 20000, 10, 20, None, [21, 64, 64, 1], "FC", "Sine",
+                               "random_correlation", seed=9)
+    t, W = sol.fetch_minibatch_device(iteration=4)
+    assert torch.all(W[:, 0] == 0) and torch.allclose(t[0, :, 0], torch.linspace(0, 1, 11, device=W.device))
+    inc = (W[:, 1:] - W[:, :-1]).reshape(-1, 20).double()
+    cov = (inc.t() @ inc / inc.shape[0]).cpu().numpy()
+    target = 0.1 * sol.correlation_matrix
+    assert np.abs(cov - target).max() <= 0.02 * np.abs(target).max()
+    assert float(inc.mean().abs()) < 5e-3
+    # a shard of the global path range reproduces the same rows bit for bit
+    t2, W2 = sol.fetch_minibatch_device(iteration=4, path_offset=7000, n_paths=500)
+    assert torch.equal(W2, W[7000:7500])
+    # a different iteration gives a different stream
+    _, W3 = sol.fetch_minibatch_device(iteration=5)
+    assert not torch.equal(W3, W)
+
+
+def test_philox_training_is_deterministic_and_learns():
+    losses = []
+    for _ in range(2):
+        sol = _bsb(512, "fp32", brownian="philox")
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            sol.train(40, 1e-3)
+        losses.append(sol.last_losses.copy())
+    assert np.array_equal(losses[0], losses[1])                # no atomics anywhere: bitwise reproducible
+    assert losses[0][-5:].mean() < 0.7 * losses[0][:5].mean()
+
+
+@pytest.mark.parametrize("M,Nn,Dd", [(1, 50, 100), (3, 1, 4), (5, 7, 1), (130, 3, 33)])
+def test_edge_shapes_match_oracle(M, Nn, Dd):
+    import dnnpde_b200 as pde
+    from oracle import fbsnn_oracle as orc
+    torch.manual_seed(1)
+    np.random.seed(1)
+    layers = [Dd + 1, 32, 32, 1]
+    Xi = np.random.uniform(0.5, 1.5, (M, Dd))                  # per-path initial states (xi_rows == M)
+    oracle = orc.OracleSolver("bsptest", Xi, 1.0, M, Nn, Dd, layers, "FC", "Tanh", squeeze_quirk=False)
+    sol = pde.BSPDETestCase(Xi, 1.0, M, Nn, Dd, None, layers, "FC", "Tanh")
+    sol.model.load_state_dict(oracle.model.state_dict())
+    t, W = oracle.fetch_minibatch()
+    ol, oX, oY, oZ, og = oracle.grads(t, W)
+    loss, X, Y, Z, g = sol.loss_grad_flat(t, W, want_Z=True)
+    assert abs(float(loss) - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-7
+    assert torch.allclose(X.cpu(), oX, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(Y.cpu(), oY, rtol=2e-5, atol=2e-6)
+    assert torch.allclose(Z.cpu(), oZ, rtol=1e-4, atol=1e-5)
+    for name, p in sol.model.named_parameters():
+        o = sol._fp.offsets[name]
+        got = g[o:o + p.numel()].view(p.shape).cpu()
+        assert float((got - og[name]).abs().max()) <= 1e-4 * float(og[name].abs().max()) + 1e-6, name
+
+
+def test_predict_broadcasts_like_the_reference():
+    import dnnpde_b200 as pde
+    torch.manual_seed(2)
+    np.random.seed(2)
+    sol = pde.BasketCallOption(np.ones((1, 6)), 1.0, 9, 5, 6, None, [7, 32, 32, 1], "FC", "Sine")
+    t, W = sol.fetch_minibatch()
+    X, Y = sol.predict(np.ones((1, 6)), t.cpu().numpy(), W.cpu().numpy())      # NumPy inputs, singleton Xi
+    assert X.shape == (9, 6, 6) and Y.shape == (9, 6, 1) and sol.M == 9
+    X1, Y1 = sol.predict(np.ones((1, 6)), t[:1], W[:1])                          # batch of one
+    assert sol.M == 1 and torch.allclose(Y1[0], Y[0], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        sol.M = 9
+        sol.loss_function(t[:, :4], W[:, :4], sol.Xi)                            # N mismatch
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Monte-Carlo pricer
+# ---------------------------------------------------------------------------------------------------------------
+def _pricer(Dm, n, corr=True, seed=3, N_steps=50, strike=1.0):
+    import dnnpde_b200 as pde
+    np.random.seed(0)
+    model = pde.BlackScholesModel(0.05, 0.2, Dm, corr)
+    return model, pde.MonteCarloPricer(model, pde.BasketOption(np.ones(Dm) / Dm, strike), 1.0, N_steps, n, seed=seed)
+
+
+@pytest.mark.parametrize("tag", ["d5", "d100", "d8_nocorr"])
+def test_mc_price_agrees_with_reference_within_standard_error(tag):
+    g, _ = gu.load("mc_pricer")
+    cfg = json.loads(str(g[f"{tag}_cfg"]))
+    model, pr = _pricer(cfg["D"], 1 << 22, cfg["corr"])
+    assert np.array_equal(model.correlation, g[f"{tag}_corr"])          # same NumPy-generated correlation matrix
+    price, se = pr.price(np.ones(cfg["D"]), return_stderr=True)
+    ref = float(g[f"{tag}_price"])                                       # the reference's own estimate at n = cfg["n"]
+    se_ref = 0.08 / math.sqrt(cfg["n"])                                  # payoff std < 0.08 for these baskets
+    assert abs(price - ref) <= 4 * math.hypot(se, se_ref), (price, ref, se, se_ref)
+    assert se < 1e-4
+
+
+def test_mc_matches_exact_moments_and_black_scholes():
+    from oracle import mc_oracle as mco
+    # strike 0 => price = exp(-rT) E[basket] exactly; variance from the closed-form covariance of correlated GBM
+    model, pr = _pricer(100, 1 << 22, True, strike=0.0)
+    price, se = pr.price(np.ones(100), return_stderr=True)
+    mean, var = mco.terminal_moments(np.ones(100), 0.05, 0.2, model.correlation, np.ones(100) / 100, 1.0)
+    assert abs(price - math.exp(-0.05) * mean) <= 4 * se
+    assert abs(se * math.sqrt(1 << 22) / math.exp(-0.05) - math.sqrt(var)) <= 0.01 * math.sqrt(var)
+    # D = 1: the Black-Scholes formula is a known answer (the reference's AnalyticalBlackScholes, exact for D = 1)
+    import dnnpde_b200 as pde
+    model1, pr1 = _pricer(1, 1 << 23, False)
+    p1, se1 = pr1.price(np.ones(1), return_stderr=True)
+    bs = pde.AnalyticalBlackScholes(0.05, 0.2, 1).price(np.ones(1), 1.0, 1.0)
+    assert abs(p1 - bs) <= 4 * se1, (p1, bs, se1)
+
+
+def test_mc_paths_and_pricer_share_streams_and_shard_exactly():
+    model, pr = _pricer(12, 40000, True, seed=17, N_steps=9)
+    S0 = np.linspace(0.8, 1.2, 12)
+    paths = model.generate_paths(S0, 1.0, 9, 40000, seed=17)
+    assert paths.shape == (40000, 10, 12) and paths.dtype == np.float64 and np.allclose(paths[:, 0], S0)
+    pay = math.exp(-0.05) * np.maximum((paths[:, -1] * (np.ones(12) / 12)).sum(1) - 1.0, 0)
+    price = pr.price(S0)
+    assert abs(price - pay.mean()) <= 2e-6 * pay.mean()        # same Philox keys: path-wise equal up to rounding
+    # sharding the global path range over "ranks" reproduces the sums (sum, sum of squares) to double round-off
+    full = pr.price_async(S0, 40000, 0, 17).cpu().numpy()
+    parts = sum(pr.price_async(S0, hi - lo, lo, 17).cpu().numpy() for lo, hi in ((0, 12345), (12345, 40000)))
+    assert np.allclose(parts, full, rtol=1e-12)
+    # log-returns are Gaussian with the right per-step variance
+    lr = np.log(paths[:, 1:] / paths[:, :-1]).reshape(-1, 12)
+    assert abs(lr.std() - 0.2 * math.sqrt(1 / 9)) < 2e-3

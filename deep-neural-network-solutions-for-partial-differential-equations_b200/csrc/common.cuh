@@ -37,11 +37,31 @@ __device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
 // internal activation codes of the TF32 variant: MUFU-based sin/cos after a two-term Cody-Waite reduction
 // (abs. error ~5e-7, far below TF32's 2^-11 operand rounding) and tanh.approx
 constexpr int kActSineFast = 3, kActTanhFast = 4;
+// 3xTF32 variant: fp32-grade sin/cos in ~20 instructions (three-term Cody-Waite reduction by pi/2 + the Cephes
+// minimax polynomials on [-pi/4, pi/4], ~1 ulp for |z| < 1e4) instead of the library sincosf (~50)
+constexpr int kActSineCW = 5;
+
+__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
+  const float k = rintf(x * 0.636619772367581343f);
+  const int q = (int)k;
+  float r = fmaf(k, -1.5703125f, x);
+  r = fmaf(k, -4.837512969970703125e-4f, r);
+  r = fmaf(k, -7.54978995489188216e-8f, r);
+  const float r2 = r * r;
+  float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+  float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2,
+                  fmaf(-0.5f, r2, 1.0f));
+  if (q & 1) { const float t = sp; sp = cp; cp = t; }
+  s = (q & 2) ? -sp : sp;
+  c = ((q + 1) & 2) ? -cp : cp;
+}
 
 // activation value g, first derivative a  (Functions/Sine.py:11-12, nn.ReLU, nn.Tanh)
 __device__ __forceinline__ void act_ga(int act, float z, float& g, float& a) {
   if (act == FBSNN_ACT_SINE) {
     sincosf(z, &g, &a);
+  } else if (act == kActSineCW) {
+    sincos_cw(z, g, a);
   } else if (act == kActSineFast) {
     const float k = rintf(z * 0.15915494309189535f);
     float r = fmaf(-k, 6.2831854820251465f, z);
@@ -61,7 +81,7 @@ __device__ __forceinline__ void act_ga(int act, float z, float& g, float& a) {
 }
 // second derivative from (g, a): sine -g, relu 0, tanh -2 g a
 __device__ __forceinline__ float act_c(int act, float g, float a) {
-  if (act == FBSNN_ACT_SINE || act == kActSineFast) return -g;
+  if (act == FBSNN_ACT_SINE || act == kActSineFast || act == kActSineCW) return -g;
   if (act == FBSNN_ACT_RELU) return 0.f;
   return -2.f * g * a;
 }

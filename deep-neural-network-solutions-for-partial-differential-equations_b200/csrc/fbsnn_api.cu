@@ -53,6 +53,8 @@ struct Plan {
   bool tf32;
   int kin, ldw;   // K extent / leading dimension of the input-width weight operands (padded to ldx in TF32 mode)
   size_t W1p, Winp[kMaxL + 2];
+  size_t Whi[kMaxL + 2], Wlo[kMaxL + 2], Winhi[kMaxL + 2], Winlo[kMaxL + 2];   // 3xTF32: exact-TF32 weight halves
+  bool x3;
   int H[kMaxL + 2];
   bool nais;
   long long rows;
@@ -139,10 +141,18 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
       const size_t hh = (size_t)p.H[l] * p.H[l];
       p.Bm[l] = take(hh), p.Rm[l] = take(hh), p.nstate[l] = take(4);
     }
+  p.x3 = s->precision == FBSNN_PREC_TF32X3;
   if (p.tf32) {
     p.W1p = take((size_t)p.H[1] * p.ldx);
     if (p.nais)
       for (int l = 2; l <= p.L; ++l) p.Winp[l] = take((size_t)p.H[l] * p.ldx);
+  }
+  if (p.x3) {
+    for (int l = 1; l <= p.L; ++l) {
+      const size_t n = (size_t)p.H[l] * (l == 1 ? p.ldx : p.H[l - 1]);
+      p.Whi[l] = take(n), p.Wlo[l] = take(n);
+      if (p.nais && l >= 2) p.Winhi[l] = take((size_t)p.H[l] * p.ldx), p.Winlo[l] = take((size_t)p.H[l] * p.ldx);
+    }
   }
   if (with_grad) {
     p.V = take(R * p.ldx);
@@ -186,6 +196,20 @@ static cudaEvent_t g_ev0[kMaxTimed], g_ev1[kMaxTimed];
 static double g_flops[kMaxTimed], g_bytes[kMaxTimed];
 static bool g_timed_tc[kMaxTimed];
 
+// 3xTF32: weight matrices that have exact-TF32 hi/lo twins in the workspace (filled by split_weights())
+struct SplitW {
+  const float* src;
+  const float* hi;
+  const float* lo;
+};
+static thread_local SplitW g_splitw[2 * (kMaxL + 2)];
+static thread_local int g_nsplitw = 0;
+static const SplitW* find_split(const float* src) {
+  for (int i = 0; i < g_nsplitw; ++i)
+    if (g_splitw[i].src == src) return &g_splitw[i];
+  return nullptr;
+}
+
 template <bool A_KC, bool B_KC>
 static bool uses_tc(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
   return s->precision != FBSNN_PREC_FP32 && tc_eligible<A_KC, B_KC>(g, nsplit);
@@ -210,9 +234,26 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
   }
   ++g_launches;
   cudaError_t e;
-  if (!tc) e = launch_gemm<A_KC, B_KC>(g, epi, nsplit, num_sms(), st);
-  else if (s->precision == FBSNN_PREC_TF32X3) e = launch_gemm_tc<A_KC, B_KC, true>(g, epi, nsplit, num_sms(), st);
-  else e = launch_gemm_tc<A_KC, B_KC, false>(g, epi, nsplit, num_sms(), st);
+  if (!tc) {
+    e = launch_gemm<A_KC, B_KC>(g, epi, nsplit, num_sms(), st);
+  } else if (s->precision == FBSNN_PREC_TF32X3) {
+    // sweeps whose weight operands all have pre-split twins: (A, W) -> (A, W_hi) [a_lo*b + a*b] + (A, W_lo) [a*b]
+    GemmArgs g2 = g;
+    bool presplit = A_KC && 2 * g.nseg <= kMaxSeg;
+    if (presplit) {
+      g2.nseg = 0;
+      for (int i = 0; i < g.nseg && presplit; ++i) {
+        const SplitW* w = find_split(g.seg[i].B);
+        if (!w) { presplit = false; break; }
+        g2.seg[g2.nseg] = g.seg[i], g2.seg[g2.nseg].B = w->hi, g2.mode[g2.nseg++] = 1;
+        g2.seg[g2.nseg] = g.seg[i], g2.seg[g2.nseg].B = w->lo, g2.mode[g2.nseg++] = 2;
+      }
+    }
+    if (presplit) e = launch_gemm_tc<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st);
+    else e = launch_gemm_tc<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st);
+  } else {
+    e = launch_gemm_tc<A_KC, B_KC, 0>(g, epi, nsplit, num_sms(), st);
+  }
   if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
   if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "%s gemm %s: %s", tc ? "tcgen05" : "simt", what, cudaGetErrorString(e));
   return 0;
@@ -266,6 +307,25 @@ static int prepare_weights(const FbsnnSpec* s, const Plan& p, const float* param
   return 0;
 }
 
+// 3xTF32: write exact-TF32 hi / lo twins of every weight matrix the sweeps use as their B operand and register them
+static int split_weights(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, cudaStream_t st) {
+  g_nsplitw = 0;
+  if (!p.x3) return 0;
+  auto one = [&](const float* src, size_t hi, size_t lo, int count) {
+    split_hi_lo_kernel<<<(count + 255) / 256, 256, 0, st>>>(src, count, ws + hi, ws + lo);
+    g_splitw[g_nsplitw++] = SplitW{src, ws + hi, ws + lo};
+  };
+  for (int l = 1; l <= p.L; ++l) {
+    one(n.W[l], p.Whi[l], p.Wlo[l], p.H[l] * (l == 1 ? p.ldx : p.H[l - 1]));
+    LAUNCH_CHECK("split_hi_lo");
+    if (p.nais && l >= 2) {
+      one(n.Win[l], p.Winhi[l], p.Winlo[l], p.H[l] * p.ldx);
+      LAUNCH_CHECK("split_hi_lo");
+    }
+  }
+  return 0;
+}
+
 // NAIS projection, once per call: Bm_l = -(s W_l^T W_l + eps I)
 static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, cudaStream_t st) {
   for (int l = 2; l <= p.L; ++l) {
@@ -285,6 +345,7 @@ static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* 
 static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, bool with_grad, cudaStream_t st) {
   const int R = (int)p.rows;
   int act = s->act_kind;
+  if (s->precision == FBSNN_PREC_TF32X3 && act == FBSNN_ACT_SINE) act = kActSineCW;
   if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_SINE) act = kActSineFast;
   if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_TANH) act = kActTanhFast;
   for (int l = 1; l <= p.L; ++l) {
@@ -533,6 +594,7 @@ static int loss_grad_impl(const FbsnnSpec* s, const float* params, float* grads,
   const Net n = bind_net(s, p, params, ws);
   if ((rc = prepare_weights(s, p, params, ws, st))) return rc;
   if (p.nais && (rc = nais_prepare(s, p, n, ws, st))) return rc;
+  if ((rc = split_weights(s, p, n, ws, st))) return rc;
   if (!W && (rc = gen_increments(s, p, ws, M, T, path_offset, seed, iteration, iter_dev, chol, st))) return rc;
   {
     const ProblemK k = problem_k(s, p);
@@ -611,13 +673,13 @@ int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const 
     bool ok = a_kc && b_kc ? tc_eligible<true, true>(g, 1) : (a_kc ? tc_eligible<true, false>(g, 1) : tc_eligible<false, false>(g, 1));
     if (!ok || (!a_kc && b_kc)) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
     if (use_tc == 2) {
-      if (a_kc && b_kc) err = launch_gemm_tc<true, true, true>(g, e, 1, num_sms(), st);
-      else if (a_kc) err = launch_gemm_tc<true, false, true>(g, e, 1, num_sms(), st);
-      else err = launch_gemm_tc<false, false, true>(g, e, 1, num_sms(), st);
+      if (a_kc && b_kc) err = launch_gemm_tc<true, true, 2>(g, e, 1, num_sms(), st);
+      else if (a_kc) err = launch_gemm_tc<true, false, 2>(g, e, 1, num_sms(), st);
+      else err = launch_gemm_tc<false, false, 2>(g, e, 1, num_sms(), st);
     } else {
-      if (a_kc && b_kc) err = launch_gemm_tc<true, true, false>(g, e, 1, num_sms(), st);
-      else if (a_kc) err = launch_gemm_tc<true, false, false>(g, e, 1, num_sms(), st);
-      else err = launch_gemm_tc<false, false, false>(g, e, 1, num_sms(), st);
+      if (a_kc && b_kc) err = launch_gemm_tc<true, true, 0>(g, e, 1, num_sms(), st);
+      else if (a_kc) err = launch_gemm_tc<true, false, 0>(g, e, 1, num_sms(), st);
+      else err = launch_gemm_tc<false, false, 0>(g, e, 1, num_sms(), st);
     }
   } else {
     if (a_kc && b_kc) err = launch_gemm<true, true>(g, e, 1, num_sms(), st);
@@ -670,6 +732,7 @@ int fbsnn_net_u(const FbsnnSpec* spec, const float* params, const float* t, cons
   const Net n = bind_net(spec, p, params, ws);
   if ((rc = prepare_weights(spec, p, params, ws, st))) return rc;
   if (p.nais && (rc = nais_prepare(spec, p, n, ws, st))) return rc;
+  if ((rc = split_weights(spec, p, n, ws, st))) return rc;
   const long long tot = rows * p.ldx;
   pack_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(t, X, rows, spec->D, p.ldx, ws + p.xin);
   LAUNCH_CHECK("pack_rows");

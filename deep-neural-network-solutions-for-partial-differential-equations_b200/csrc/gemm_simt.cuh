@@ -20,8 +20,12 @@ struct GemmSeg {
   const float* B;
   int lda, ldb, K;
 };
+constexpr int kMaxSeg = 8;
 struct GemmArgs {
-  GemmSeg seg[4];
+  GemmSeg seg[kMaxSeg];
+  // tcgen05 3xTF32 only: 0 = one MMA a*b; 1 = B is an exact-TF32 "hi" matrix, A is split in-kernel: a_lo*b + a*b;
+  // 2 = B is the matching "lo" matrix: a*b only; 3 = both operands split in-kernel: a_lo*b + a*b_lo + a*b
+  unsigned char mode[kMaxSeg];
   int nseg;
   int M, N;
   int Nb;      // valid columns of the B operands (<= N; columns in [Nb, N) read as zero)

@@ -34,8 +34,8 @@ constexpr int EPI_TILE_BYTES = 32 * 32 * 4;      // per-warp 32x32 fp32 transpos
 constexpr uint32_t kSpinLimit = 1u << 24;       // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct TmSet {
-  CUtensorMap a[4];
-  CUtensorMap b[4];
+  CUtensorMap a[kMaxSeg];
+  CUtensorMap b[kMaxSeg];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,29 +116,38 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b
       : "r"(taddr))
 
 // ----------------------------------------------------------------------------------------------------
-// SPLIT3 = fp32-grade accuracy on the tensor cores ("3xTF32"): every operand tile x is used as hi = trunc_tf32(x)
-// (what the UMMA reads from the fp32 container anyway) and lo = x - hi, written by four splitter warps into a second
-// pair of smem tiles as soon as the TMA lands; three MMAs per k-step accumulate lo*hi + hi*lo + hi*hi in TMEM.
-// The dropped lo*lo term and the truncation of lo are ~2^-21 relative.  The kernel stays HBM-bound (the tensor
-// pipe was 13-39 % busy with one MMA per k-step), so this costs little time; it costs shared memory: 2 stages.
-template <bool SPLIT3>
+// SPLIT > 0 = fp32-grade accuracy on the tensor cores ("3xTF32"): an operand x is used as hi = trunc_tf32(x) (what
+// the UMMA reads from the fp32 container anyway) and lo = x - hi; the products lo*hi + hi*lo + hi*hi are accumulated
+// in TMEM, the dropped lo*lo term and the truncation of lo are ~2^-21 relative.  Four splitter warps write the lo
+// tiles into extra shared memory as soon as the TMA lands.  The kernel stays HBM-bound (the tensor pipe was 13-39 %
+// busy with one MMA per k-step); what 3xTF32 costs is shared memory, i.e. pipeline depth:
+//   SPLIT = 1 (sweeps): the weight operand arrives pre-split from global memory as two exact-TF32 matrices W_hi,
+//              W_lo, used as two K-concatenated segments (A, W_hi) [2 MMAs] and (A, W_lo) [1 MMA]; only A_lo needs
+//              a tile -> 64 KB per stage, 3 stages.  The A tile is fetched twice (second time from L2).
+//   SPLIT = 2 (weight gradients, both operands are row arrays): A_lo and B_lo tiles -> 96 KB per stage, 2 stages.
+template <int SPLIT>
 struct Cfg {
-  static constexpr int STAGES = SPLIT3 ? 2 : 3;
-  static constexpr int SPLIT_WARPS = SPLIT3 ? 4 : 0;
+  static constexpr int STAGES = SPLIT == 2 ? 2 : 3;
+  static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
   static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
+  // SPLIT == 2 (weight gradients): the epilogue warps are idle during the long K loop of a work item, so they
+  // join the splitters (12 warps) and run the (tiny) epilogue afterwards
+  static constexpr int SPLIT_TEAM_WARPS = SPLIT == 2 ? SPLIT_WARPS + 8 : SPLIT_WARPS;
   static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
-  static constexpr int STAGE_BYTES = (A_STAGE_BYTES + B_STAGE_BYTES) * (SPLIT3 ? 2 : 1);
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES + (SPLIT >= 1 ? A_STAGE_BYTES : 0) +
+                                     (SPLIT == 2 ? B_STAGE_BYTES : 0);   // [A][B]([A_lo]([B_lo]))
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES + 1024 /*align*/ + 256;
 };
 
-template <bool A_MN, bool B_MN, bool SPLIT3, class Epi>
-__global__ void __launch_bounds__(Cfg<SPLIT3>::NUM_THREADS, 1)
+template <bool A_MN, bool B_MN, int SPLIT, class Epi>
+__global__ void __launch_bounds__(Cfg<SPLIT>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi, const int num_mtiles, const int nsplit) {
-  using C = Cfg<SPLIT3>;
+  using C = Cfg<SPLIT>;
   constexpr int STAGES = C::STAGES;
+  constexpr bool SPLIT3 = SPLIT > 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  // stage layout: [A 16K][B 32K]([A_lo 16K][B_lo 32K])
+  // stage layout: [A 16K][B 32K]([A_lo 16K]([B_lo 32K]))
   float* epi_tiles = (float*)(smem + STAGES * C::STAGE_BYTES);
   uint64_t* bars = (uint64_t*)(smem + STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES);
   uint64_t* full = bars;               // [STAGES]  TMA bytes landed
@@ -157,7 +166,8 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.a[s]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b[s]) : "memory");
     }
-    for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1), mbar_init(&sdone[i], 4);
+    for (int i = 0; i < STAGES; ++i)
+      mbar_init(&full[i], 1), mbar_init(&empty[i], 1), mbar_init(&sdone[i], C::SPLIT_TEAM_WARPS);
     for (int i = 0; i < 2; ++i) mbar_init(&tfull[i], 1), mbar_init(&tempty[i], NUM_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -225,17 +235,17 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
             const uint32_t a = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t b = a + A_STAGE_BYTES;
             const uint32_t alo = a + A_STAGE_BYTES + B_STAGE_BYTES, blo = alo + A_STAGE_BYTES;
+            const int mode = SPLIT == 2 ? 3 : (SPLIT == 1 ? g.mode[s] : 0);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               auto da = [&](uint32_t base) { return A_MN ? make_desc(base + k * 1024, 4096, 512, 1) : make_desc(base + k * 32, 16, 1024, 2); };
               auto db = [&](uint32_t base) { return B_MN ? make_desc(base + k * 1024, 4096, 512, 1) : make_desc(base + k * 32, 16, 1024, 2); };
-              if (SPLIT3) {
+              if (mode & 1) {   // modes 1, 3: a_lo * b
                 umma_tf32(tmem_d, da(alo), db(b), idesc, first ? 0u : 1u);
-                umma_tf32(tmem_d, da(a), db(blo), idesc, 1u);
-                umma_tf32(tmem_d, da(a), db(b), idesc, 1u);
-              } else {
-                umma_tf32(tmem_d, da(a), db(b), idesc, first ? 0u : 1u);
+                first = 0;
               }
+              if (SPLIT == 2) umma_tf32(tmem_d, da(a), db(blo), idesc, 1u);
+              umma_tf32(tmem_d, da(a), db(b), idesc, first ? 0u : 1u);
               first = 0;
             }
             umma_commit(&empty[stage]);   // smem slot free once these MMAs have read it
@@ -245,62 +255,25 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
         umma_commit(&tfull[acc]);         // accumulator complete
       }
     }
-  } else if (SPLIT3 && warp < C::EPI_WARP0) {
-    // ===================== splitter warps (SPLIT3): lo = x - trunc_tf32(x) for both operand tiles ==============
-    const int ts = threadIdx.x - 64;
-    const int nA4 = A_STAGE_BYTES / 16, nB4 = N * BK * 4 / 16;
-    uint32_t stage = 0, phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int split = w / num_mtiles;
-      for (int s = 0; s < g.nseg; ++s) {
-        for (int k0 = kbeg(s, split), ke = kend(s, split); k0 < ke; k0 += BK) {
-          mbar_wait(&full[stage], phase);
-          const float4* a = (const float4*)(smem + stage * C::STAGE_BYTES);
-          float4* lo = (float4*)(smem + stage * C::STAGE_BYTES + A_STAGE_BYTES + B_STAGE_BYTES);
-          // A tile [0, nA4) maps to lo[0, nA4); B tile starts at A_STAGE_BYTES in both halves
-          // A and B tiles are contiguous ([A 16K][B N*128]) in both halves of the stage: one flat loop, 8 loads in
-          // flight per thread
-          const int n4 = nA4 + nB4;
-          for (int i0 = ts; i0 < n4; i0 += 128 * 8) {
-            float4 x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (i0 + u * 128 < n4) x[u] = a[i0 + u * 128];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (i0 + u * 128 < n4) {
-                float4 l;
-                l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
-                l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
-                l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
-                l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
-                lo[i0 + u * 128] = l;
-              }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sdone[stage]);
-          if (++stage == STAGES) stage = 0, phase ^= 1;
-        }
-      }
-    }
   } else {
-    // ===================== epilogue warps =====================
-    // TMEM hands each lane one accumulator ROW; the row arrays in global memory want a warp on one row's
+    // ===================== splitter and epilogue warps =====================
+    // Epilogue: TMEM hands each lane one accumulator ROW; the row arrays in global memory want a warp on one row's
     // contiguous columns.  Each 32x32 chunk is therefore transposed through a warp-private XOR-swizzled smem tile,
     // after which 8 lanes cover 128 B of one row and a warp-wide access touches 4 full cache lines instead of 32.
+    const bool is_epi = warp >= C::EPI_WARP0;
     const int e = warp - C::EPI_WARP0;
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int half = e >> 2;               // column half
     const int ncol = N >> 1;
-    float* tile = epi_tiles + e * (EPI_TILE_BYTES / 4);
+    float* tile = epi_tiles + (is_epi ? e : 0) * (EPI_TILE_BYTES / 4);
     const int sub = lane >> 3, c4 = lane & 7;
     constexpr bool kColsum = Epi::kColsum;
     float4 csum[4];                        // per-thread column sums of zbar: chunk x 4 columns (N/2 <= 128)
 #pragma unroll
     for (int i = 0; i < 4; ++i) csum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+
+    // drain the accumulator of work item w (local index it) through the fused epilogue
+    auto drain = [&](int w, uint32_t it) {
       const int mt = w % num_mtiles;
       const int split = w / num_mtiles;
       (void)split;
@@ -357,11 +330,65 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+    };
+
+    // lo = x - trunc_tf32(x) for the operand tiles of every k-block of work item w (SPLIT > 0)
+    constexpr int TEAM = 32 * (C::SPLIT_TEAM_WARPS > 0 ? C::SPLIT_TEAM_WARPS : 1);
+    uint32_t sstage = 0, sphase = 0;
+    auto split_item = [&](int w) {
+      const int ts = threadIdx.x - 64;
+      const int nA4 = A_STAGE_BYTES / 16, nB4 = N * BK * 4 / 16;
+      const int split = w / num_mtiles;
+      for (int s = 0; s < g.nseg; ++s) {
+        for (int k0 = kbeg(s, split), ke = kend(s, split); k0 < ke; k0 += BK) {
+          mbar_wait(&full[sstage], sphase);
+          const float4* a = (const float4*)(smem + sstage * C::STAGE_BYTES);
+          float4* lo = (float4*)(smem + sstage * C::STAGE_BYTES + A_STAGE_BYTES + B_STAGE_BYTES);
+          // A and B tiles are contiguous ([A 16K][B N*128]) and so are their lo twins: one flat loop, 8 loads in
+          // flight per thread.  SPLIT == 1: only A (mode 1 segments), nothing for the W_lo segments (mode 2).
+          const int n4 = SPLIT == 2 ? nA4 + nB4 : (g.mode[s] == 1 ? nA4 : 0);
+          for (int i0 = ts; i0 < n4; i0 += TEAM * 8) {
+            float4 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i0 + u * TEAM < n4) x[u] = a[i0 + u * TEAM];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i0 + u * TEAM < n4) {
+                float4 l;
+                l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
+                l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
+                l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
+                l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
+                lo[i0 + u * TEAM] = l;
+              }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sdone[sstage]);
+          if (++sstage == STAGES) sstage = 0, sphase ^= 1;
+        }
+      }
+    };
+
+    if (SPLIT == 2) {
+      // weight gradients: all 12 warps split the K loop of a work item, then the epilogue warps drain it
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        split_item(w);
+        if (is_epi) drain(w, it);
+      }
+    } else if (SPLIT == 1 && !is_epi) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) split_item(w);
+    } else {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) drain(w, it);
     }
+
     if constexpr (kColsum) {
       // fused bias gradient: per-CTA column sums of zbar -> colpart[blockIdx.x][col]; fixed reduction order
       // (4 row groups of a warp by shuffle, then the 4 lane-quarter warps of a column half through smem).
-      if (epi.colpart) {
+      if (epi.colpart && is_epi) {
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float4 t = csum[ch];
@@ -432,7 +459,7 @@ inline bool make_map(CUtensorMap* m, const float* base, long long inner, long lo
 
 template <bool A_KC, bool B_KC>
 inline bool tc_eligible(const GemmArgs& g, int nsplit) {
-  if (g.N < 64 || g.N > 256 || g.N % 64 || g.nseg < 1 || g.nseg > 4) return false;
+  if (g.N < 64 || g.N > 256 || g.N % 64 || g.nseg < 1 || g.nseg > kMaxSeg) return false;
   if (!A_KC && B_KC) return false;   // (MN-major A, K-major B) never occurs in the sweeps
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
@@ -444,10 +471,10 @@ inline bool tc_eligible(const GemmArgs& g, int nsplit) {
   return true;
 }
 
-template <bool A_KC, bool B_KC, bool SPLIT3, class Epi>
+template <bool A_KC, bool B_KC, int SPLIT, class Epi>
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
   constexpr bool A_MN = !A_KC, B_MN = !B_KC;
-  using C = tc::Cfg<SPLIT3>;
+  using C = tc::Cfg<SPLIT>;
   tc::TmSet tm;
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
@@ -458,8 +485,8 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit,
     else      ok = ok && tc::make_map(&tm.b[s], sg.B, sg.K, g.Nb, sg.ldb, 32, g.N, false);  // W[n][k]
     if (!ok) return cudaErrorInvalidValue;
   }
-  for (int s = g.nseg; s < 4; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];
-  auto kern = tc::gemm_tc_kernel<A_MN, B_MN, SPLIT3, Epi>;
+  for (int s = g.nseg; s < kMaxSeg; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];
+  auto kern = tc::gemm_tc_kernel<A_MN, B_MN, SPLIT, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);

@@ -139,6 +139,16 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, int rows, int col
   dst[i] = c < cols ? src[r * cols + c] : 0.f;
 }
 
+// 3xTF32 variant: hi = x with the 13 low mantissa bits cleared (exactly what the tensor core reads), lo = x - hi
+__global__ void split_hi_lo_kernel(const float* __restrict__ src, int n, float* __restrict__ hi, float* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = src[i];
+  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = x - h;
+}
+
 // u[r] = h_L[r,:] . wout + bout      (one warp per row)
 __global__ void head_kernel(const float* __restrict__ h, int ld, int H, const float* __restrict__ wout,
                             const float* __restrict__ bout, long long rows, float* __restrict__ u) {

@@ -262,7 +262,8 @@ def measure_roofline(c, args, sol, batches, ms_per_step, m_loc):
     # rates alongside ("Roofline").
     return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
             "traffic": None,
-            "kernel": "gemm_tc_kernel (tcgen05 kind::tf32, TMA, TMEM)" if is_tc else "gemm_simt_kernel (fp32 FMA)",
+            "kernel": (f"gemm_tc_kernel (tcgen05 kind::tf32{' x3 hi/lo split' if args.precision == 'tf32x3' else ''}, "
+                       "TMA, TMEM)") if is_tc else "gemm_simt_kernel (fp32 FMA)",
             "launches_per_step": n_dense, "dense_ms_per_step": dense_ms, "dense_share_of_step": dense_ms / ms_per_step,
             "algorithmic_bytes_per_step": dense_bytes, "tflops": tflops, "tf32_peak_tflops": tf32_peak,
             "tensor_frac": tflops / tf32_peak, "tc_launches": int(out[3]),
@@ -350,7 +351,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "iters/s", "n_gpus": c.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "vs_baseline": None, "data": "synthetic",
+        "dtype": {"tf32": "tf32", "tf32x3": "tf32x3 (fp32-grade: hi/lo-split TF32 MMAs, fp32 accumulate)",
+                  "fp32": "f32"}[args.precision],
         "config": workload_config(args), "clocks": clk, "gpu_launches": launches, "final_loss": final_loss,
     }
     line["roofline"] = measure_roofline(c, args, sol, batches, ms_per_step, m_loc)
@@ -358,15 +361,24 @@ def run_ours(args):
         line["e2e"] = measure_e2e(c, args, sol, batches)
     del sol
     torch.cuda.empty_cache()
-    if args.precision == "tf32" and not args.skip_fp32:
-        # the parity-grade fp32 SIMT variant on the same workload, fewer steps (it is ~4x slower)
-        a2 = argparse.Namespace(**vars(args))
-        a2.precision, a2.steps = "fp32", max(2, args.steps // 3)
-        sol2, _, _ = make_solver(c, a2, batches)
-        ms2, _, _, _ = measure_value(c, a2, sol2, batches)
-        line["fp32_variant"] = {"value": 1e3 / ms2, "unit": "iters/s", "ms_per_step": ms2, "steps": a2.steps,
-                                "kernel": "gemm_simt_kernel (fp32 FMA), tolerances of tests/test_parity_gpu.py::TOL"}
-        del sol2
+    if not args.skip_fp32:
+        # the other arithmetic variants on the same workload and minibatches (tests/test_parity_gpu.py states
+        # each variant's tolerance): single-pass TF32 (faster, looser) and SIMT fp32 (slower, tightest)
+        notes = {"tf32": "tcgen05 kind::tf32 single pass; tolerance TOL_TF32 (loss 1e-2, Z 5e-2)",
+                 "tf32x3": "tcgen05 3xTF32 (hi/lo split), fp32-grade; tolerance TOL_X3 (loss 1e-4, Z 5e-5)",
+                 "fp32": "gemm_simt_kernel fp32 FMA; tolerance TOL (loss 2e-5, Z 1e-5)"}
+        line["variants"] = {args.precision: {"value": 1e3 / ms_per_step, "ms_per_step": ms_per_step,
+                                             "note": notes[args.precision]}}
+        for prec in ("tf32x3", "tf32", "fp32"):
+            if prec == args.precision:
+                continue
+            a2 = argparse.Namespace(**vars(args))
+            a2.precision, a2.steps = prec, (max(2, args.steps // 3) if prec == "fp32" else args.steps)
+            sol2, _, _ = make_solver(c, a2, batches)
+            ms2, _, _, _ = measure_value(c, a2, sol2, batches)
+            line["variants"][prec] = {"value": 1e3 / ms2, "ms_per_step": ms2, "steps": a2.steps, "note": notes[prec]}
+            del sol2
+            torch.cuda.empty_cache()
     del batches
     torch.cuda.empty_cache()
     if not args.skip_mc:
@@ -395,9 +407,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=65536, help="global number of Brownian paths M")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32x3"],
-                    help="tf32: tcgen05 tensor-core variant (stated tolerance, tests/test_parity_gpu.py); "
-                         "fp32: SIMT parity-grade variant")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"],
+                    help="tf32x3 (default): tcgen05 tensor cores with hi/lo operand split, fp32-grade results; "
+                         "tf32: single-pass tcgen05 (looser stated tolerance); fp32: SIMT FMA (tightest parity)")
     ap.add_argument("--mc-paths", type=int, default=1 << 28)
     ap.add_argument("--cpu-sample-paths", type=int, default=256)
     ap.add_argument("--skip-mc", action="store_true")

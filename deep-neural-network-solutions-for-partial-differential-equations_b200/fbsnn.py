@@ -116,7 +116,9 @@ class FBSNN(ABC):
         self.correlation_type = correlation_type
         self.correlation_matrix = self.generate_correlation_matrix(D)
 
-        self.precision = extras.get("precision", "fp32")
+        # arithmetic variant of the dense layers: "tf32x3" (default; tensor cores, fp32-grade), "fp32" (SIMT FMA,
+        # tightest parity), "tf32" (single-pass tensor cores, looser stated tolerance)
+        self.precision = extras.get("precision", "tf32x3")
         if self.precision not in S.PRECISION:
             raise ValueError(f"precision {self.precision!r} not in {sorted(S.PRECISION)}")
         self.n_schedule = extras.get("n_schedule")

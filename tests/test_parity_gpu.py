@@ -43,7 +43,8 @@ def test_train_api_matches_reference_graph():
     oracle = gu.rebuild_inputs(meta0, g0)
     np.random.seed(meta["numpy_seed"])
     D, M, N = meta["D"], meta["M"], meta["N"]
-    sol = pde.BlackScholesBarenblatt(gu.make_xi("bsb", D), 1.0, M, N, D, [D + 1] + 4 * [256] + [1], "FC", "Sine")
+    sol = pde.BlackScholesBarenblatt(gu.make_xi("bsb", D), 1.0, M, N, D, [D + 1] + 4 * [256] + [1], "FC", "Sine",
+                                     precision="fp32")
     sol.model.load_state_dict(oracle.model.state_dict())
     graph = sol.train(3, 1e-3)
     assert graph.shape == (2, 1) and graph[0, 0] == 0

@@ -5,6 +5,7 @@ The directory name is not a Python identifier; import it with
 or through the `dnnpde_b200` alias module at the repository root.
 """
 from . import _lib, parallel, spec
+from .drivers import PredictionGenerator, TrainingPhases
 from .fbsnn import FBSNN
 from .mc_pricer import (AnalyticalBlackScholes, BasketOption, BlackScholesModel, CorrelationMatrix,
                         MonteCarloPricer)
@@ -17,4 +18,5 @@ build = _lib.build
 __all__ = ["FBSNN", "Sine", "Naisnet", "BlackScholesBarenblatt", "BasketCallOption", "BSPDETestCase",
            "CallOption1D", "CallOptionND", "HamiltonJacobiBellman", "u_exact", "CorrelationMatrix",
            "BlackScholesModel", "BasketOption", "MonteCarloPricer", "AnalyticalBlackScholes", "build",
+           "TrainingPhases", "PredictionGenerator",
            "parallel", "spec"]

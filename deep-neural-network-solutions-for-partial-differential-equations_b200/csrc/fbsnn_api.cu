@@ -776,7 +776,7 @@ int fbsnn_train_step(const FbsnnSpec* spec, const FbsnnAdam* host_hp, float* par
                      size_t workspace_bytes, float* X_out, float* Y_out, float* loss_out, void* stream) {
   if (!opt_state) return fail(FBSNN_E_BADARG, "opt_state is null");
   int rc = loss_grad_impl(spec, params, grads, t, W, Xi, xi_rows, n_paths, T, path_offset, seed, iteration,
-                          (const long long*)opt_state, chol, workspace, workspace_bytes, X_out, Y_out, nullptr,
+                          &((const OptState*)opt_state)->rng_iter, chol, workspace, workspace_bytes, X_out, Y_out, nullptr,
                           loss_out, true, (cudaStream_t)stream);
   if (rc) return rc;
   return adam_impl(host_hp, params, grads, exp_avg, exp_avg_sq, spec->n_params, opt_state,

@@ -125,24 +125,29 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b
 //              W_lo, used as two K-concatenated segments (A, W_hi) [2 MMAs] and (A, W_lo) [1 MMA]; only A_lo needs
 //              a tile -> 64 KB per stage, 3 stages.  The A tile is fetched twice (second time from L2).
 //   SPLIT = 2 (weight gradients, both operands are row arrays): A_lo and B_lo tiles -> 96 KB per stage, 2 stages.
-template <int SPLIT>
+// BN = widest output tile of a CTA (256, or 128 for the SPLIT == 2 weight-gradient kernel: with 128 columns a
+// stage is 64 KB and three fit, which the serial TMA -> split -> MMA chain of that kernel needs; the two column
+// halves are separate work items that share their operand rows through L2).
+template <int SPLIT, int BN = 256>
 struct Cfg {
-  static constexpr int STAGES = SPLIT == 2 ? 2 : 3;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGES = (SPLIT == 2 && BN == 256) ? 2 : 3;
   static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
   static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
   // SPLIT == 2 (weight gradients): the epilogue warps are idle during the long K loop of a work item, so they
   // join the splitters (12 warps) and run the (tiny) epilogue afterwards
   static constexpr int SPLIT_TEAM_WARPS = SPLIT == 2 ? SPLIT_WARPS + 8 : SPLIT_WARPS;
   static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES + (SPLIT >= 1 ? A_STAGE_BYTES : 0) +
-                                     (SPLIT == 2 ? B_STAGE_BYTES : 0);   // [A][B]([A_lo]([B_lo]))
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES + (SPLIT >= 1 ? A_STAGE_BYTES : 0) +
+                                     (SPLIT == 2 ? B_BYTES : 0);   // [A][B]([A_lo]([B_lo]))
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES + 1024 /*align*/ + 256;
 };
 
-template <bool A_MN, bool B_MN, int SPLIT, class Epi>
-__global__ void __launch_bounds__(Cfg<SPLIT>::NUM_THREADS, 1)
+template <bool A_MN, bool B_MN, int SPLIT, int BN, class Epi>
+__global__ void __launch_bounds__(Cfg<SPLIT, BN>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi, const int num_mtiles, const int nsplit) {
-  using C = Cfg<SPLIT>;
+  using C = Cfg<SPLIT, BN>;
+  constexpr int B_STAGE_BYTES = C::B_BYTES;
   constexpr int STAGES = C::STAGES;
   constexpr bool SPLIT3 = SPLIT > 0;
   extern __shared__ uint8_t smem_raw[];
@@ -158,8 +163,10 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
   uint32_t* tmem_slot = (uint32_t*)(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = g.N;
-  const int num_work = num_mtiles * nsplit;
+  const int N = g.N < BN ? g.N : BN;                    // columns of one CTA tile
+  const int num_ntiles = (g.N + BN - 1) / BN;
+  const int num_mn = num_mtiles * num_ntiles;           // work id = (split, nt, mt), mt fastest
+  const int num_work = num_mn * nsplit;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nseg; ++s) {
@@ -192,8 +199,8 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       uint32_t stage = 0, phase = 0;
       const uint32_t bytes = A_STAGE_BYTES + (uint32_t)N * BK * 4;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int mt = w % num_mtiles, split = w / num_mtiles;
-        const int m0 = mt * BM;
+        const int mt = w % num_mtiles, nt = (w % num_mn) / num_mtiles, split = w / num_mn;
+        const int m0 = mt * BM, n0 = nt * BN;
         for (int s = 0; s < g.nseg; ++s) {
           for (int k0 = kbeg(s, split), ke = kend(s, split); k0 < ke; k0 += BK) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -207,9 +214,9 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
               tma_load_2d(a, &tm.a[s], &full[stage], k0, m0);
             }
             if (B_MN) {
-              for (int c = 0; c < N / 32; ++c) tma_load_2d(b + c * 4096, &tm.b[s], &full[stage], 32 * c, k0);
+              for (int c = 0; c < N / 32; ++c) tma_load_2d(b + c * 4096, &tm.b[s], &full[stage], n0 + 32 * c, k0);
             } else {
-              tma_load_2d(b, &tm.b[s], &full[stage], k0, 0);
+              tma_load_2d(b, &tm.b[s], &full[stage], k0, n0);
             }
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
@@ -222,7 +229,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       const uint32_t idesc = make_idesc(N, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-        const int split = w / num_mtiles;
+        const int split = w / num_mn;
         const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], accphase ^ 1);
         tc_fence_after();
@@ -275,7 +282,8 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
     // drain the accumulator of work item w (local index it) through the fused epilogue
     auto drain = [&](int w, uint32_t it) {
       const int mt = w % num_mtiles;
-      const int split = w / num_mtiles;
+      const int n0 = ((w % num_mn) / num_mtiles) * BN;
+      const int split = w / num_mn;
       (void)split;
       const uint32_t acc = it & 1, accphase = (it >> 1) & 1;
       mbar_wait(&tfull[acc], accphase);
@@ -283,10 +291,11 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       const int r0 = mt * BM + q * 32;
 #pragma unroll 1
       for (int ch = 0; ch * 32 < ncol; ++ch) {
-        const int c0 = half * ncol + ch * 32;
+        const int ct = half * ncol + ch * 32;   // column inside the CTA tile (TMEM column)
+        const int c0 = n0 + ct;                 // global output column
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ct;
         FBSNN_TMEM_LD32(taddr, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -338,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
     auto split_item = [&](int w) {
       const int ts = threadIdx.x - 64;
       const int nA4 = A_STAGE_BYTES / 16, nB4 = N * BK * 4 / 16;
-      const int split = w / num_mtiles;
+      const int split = w / num_mn;
       for (int s = 0; s < g.nseg; ++s) {
         for (int k0 = kbeg(s, split), ke = kend(s, split); k0 < ke; k0 += BK) {
           mbar_wait(&full[sstage], sphase);
@@ -471,10 +480,10 @@ inline bool tc_eligible(const GemmArgs& g, int nsplit) {
   return true;
 }
 
-template <bool A_KC, bool B_KC, int SPLIT, class Epi>
+template <bool A_KC, bool B_KC, int SPLIT, class Epi, int BN = 256>
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
   constexpr bool A_MN = !A_KC, B_MN = !B_KC;
-  using C = tc::Cfg<SPLIT>;
+  using C = tc::Cfg<SPLIT, BN>;
   tc::TmSet tm;
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
@@ -482,11 +491,11 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit,
     if (A_MN) ok = tc::make_map(&tm.a[s], sg.A, g.M, sg.K, sg.lda, 32, 32, true);       // P[k = rows][m]
     else      ok = tc::make_map(&tm.a[s], sg.A, sg.K, g.M, sg.lda, 32, tc::BM, false);  // X[m = rows][k]
     if (B_MN) ok = ok && tc::make_map(&tm.b[s], sg.B, g.Nb, sg.K, sg.ldb, 32, 32, true);    // W[k][n] / Q[k = rows][n]
-    else      ok = ok && tc::make_map(&tm.b[s], sg.B, sg.K, g.Nb, sg.ldb, 32, g.N, false);  // W[n][k]
+    else      ok = ok && tc::make_map(&tm.b[s], sg.B, sg.K, g.Nb, sg.ldb, 32, g.N < BN ? g.N : BN, false);  // W[n][k]
     if (!ok) return cudaErrorInvalidValue;
   }
   for (int s = g.nseg; s < kMaxSeg; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];
-  auto kern = tc::gemm_tc_kernel<A_MN, B_MN, SPLIT, Epi>;
+  auto kern = tc::gemm_tc_kernel<A_MN, B_MN, SPLIT, BN, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -494,7 +503,7 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit,
     attr_set = true;
   }
   const int mtiles = (g.M + tc::BM - 1) / tc::BM;
-  const int work = mtiles * nsplit;
+  const int work = mtiles * ((g.N + BN - 1) / BN) * nsplit;
   const int grid = work < num_sms ? work : num_sms;
   kern<<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(tm, g, epi, mtiles, nsplit);
   return cudaGetLastError();

@@ -424,11 +424,12 @@ __global__ void nais_project_bwd_kernel(const float* __restrict__ Bbar, const fl
 // ----------------------------------------------------------------------------------------------------
 // clip_grad_norm_(max_norm) + Adam (torch.optim.Adam defaults; with_corr_high_dimension_pde.py:424-425)
 // opt_state (device, 64 B): [0] int64 step | [8] float clip_coef | [12] float step_size | [16] float bc2_sqrt
-//                            | [20] float grad_norm
+//                            | [20] float grad_norm | [24] int64 Philox iteration counter (advanced with the step)
 // ----------------------------------------------------------------------------------------------------
 struct OptState {
-  long long step;
+  long long step;                                    // Adam step (reset when a new optimiser is created)
   float clip_coef, step_size, bc2_sqrt, grad_norm;
+  long long rng_iter;                                // Philox iteration counter of fbsnn_train_step (never reset)
 };
 
 __global__ void gradsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
@@ -452,6 +453,7 @@ __global__ void opt_prepare_kernel(const float* __restrict__ part, int npart, Fb
     const double bc1 = 1.0 - pow(hp.beta1, (double)step);
     const double bc2 = 1.0 - pow(hp.beta2, (double)step);
     st->step = step;
+    st->rng_iter += 1;
     st->clip_coef = coef;
     st->step_size = (float)(hp.lr / bc1);
     st->bc2_sqrt = (float)sqrt(bc2);

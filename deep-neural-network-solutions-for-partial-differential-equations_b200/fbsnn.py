@@ -71,8 +71,8 @@ class FBSNN(ABC):
         # two reference arities: (layers, mode, activation) and (Mm, layers, mode, activation[, correlation_type])
         names_short = ["layers", "mode", "activation"]
         names_long = ["Mm", "layers", "mode", "activation", "correlation_type"]
-        extras = {k: kw.pop(k) for k in ("precision", "n_schedule", "brownian", "seed", "device", "data_parallel")
-                  if k in kw}
+        extras = {k: kw.pop(k) for k in ("precision", "n_schedule", "brownian", "seed", "device", "data_parallel",
+                                          "cuda_graph") if k in kw}
         if len(args) == 3 or (len(args) < 3 and "Mm" not in kw and len(args) + len(kw) == 3):
             vals = dict(zip(names_short, args))
             self._arity = "short"
@@ -133,6 +133,8 @@ class FBSNN(ABC):
         self._chol_dev = None
         self._opt_state = None
         self._n_train_calls = 0
+        self._graphs = {}
+        self.use_cuda_graph = bool(extras.get("cuda_graph", True))
 
     # ------------------------------------------------------------------------------------------------
     # host-side pieces kept verbatim in meaning
@@ -249,6 +251,7 @@ class FBSNN(ABC):
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need.value:
             self._ws[key] = None
+            self._graphs.clear()            # captured graphs hold the old workspace address
             ws = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         off = (-ws.data_ptr()) % 256
@@ -418,7 +421,7 @@ class FBSNN(ABC):
                     t_b, W_b = self.fetch_minibatch()
                 else:
                     t_b = W_b = None
-                X, Y = self.training_step(t_b, W_b, loss_buf[k:k + 1], want_X=track_min, iteration=k)
+                X, Y = self._step(t_b, W_b, loss_buf[k:k + 1], track_min, k)
                 y0_buf[k] = Y[0, 0, 0]
                 if track_min:   # reference semantics: a host read of the loss every iteration (with_corr...:431-433)
                     lv = float(loss_buf[k])
@@ -451,10 +454,51 @@ class FBSNN(ABC):
         """Fresh Adam state, as the reference builds a new optimiser in every train() call."""
         fp = self._fp
         fp.exp_avg.zero_(), fp.exp_avg_sq.zero_()
-        self._opt_state = torch.zeros(S.OPT_STATE_BYTES, dtype=torch.uint8, device=self.device)
+        if self._opt_state is None:
+            self._opt_state = torch.zeros(S.OPT_STATE_BYTES, dtype=torch.uint8, device=self.device)
+        self._opt_state[:24].zero_()       # Adam step counter; the Philox iteration counter at byte 24 lives on
         self.optimizer = {"type": "Adam", "lr": learning_rate, "betas": (0.9, 0.999), "eps": 1e-8}
         self._hp = S.FbsnnAdam(learning_rate, 0.9, 0.999, 1e-8, self._clip_norm if self._clip_norm else 0.0)
         self._n_train_calls += 1
+
+    def _step(self, t_b, W_b, loss_out, want_X, k, alias_inputs=False):
+        """training_step through a captured CUDA graph when possible (single GPU): the ~38 kernels of an iteration
+        are replayed with one launch, which is what bounds small-M steps.  The Adam step and Philox iteration
+        counters live on the device, so a replay is a genuinely new iteration."""
+        if not self.use_cuda_graph or (self.data_parallel and parallel.is_distributed()):
+            return self.training_step(t_b, W_b, loss_out, want_X=want_X, iteration=k)
+        host_batch = W_b is not None
+        key = (self.M, self.N, self.precision, bool(want_X), host_batch, self._hp.lr, self._hp.max_grad_norm,
+               self.seed, (t_b.data_ptr(), W_b.data_ptr()) if (alias_inputs and host_batch) else None)
+        gs = self._graphs.get(key)
+        if gs is None:
+            dev = self.device
+            gs = {"loss": torch.zeros(1, device=dev)}
+            if host_batch and alias_inputs:     # caller keeps (t_b, W_b) alive and in place: read them directly
+                gs["t"], gs["W"] = t_b, W_b
+            elif host_batch:
+                gs["t"], gs["W"] = torch.empty_like(t_b), torch.empty_like(W_b)
+                gs["t"].copy_(t_b), gs["W"].copy_(W_b)
+            # capture needs a warm-up run on a side stream; keep it side-effect free by restoring the state
+            fp = self._fp
+            saved = [x.clone() for x in (fp.flat, fp.exp_avg, fp.exp_avg_sq, self._opt_state)]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.training_step(gs.get("t"), gs.get("W"), gs["loss"], want_X=want_X)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gs["X"], gs["Y"] = self.training_step(gs.get("t"), gs.get("W"), gs["loss"], want_X=want_X)
+            for dst, src in zip((fp.flat, fp.exp_avg, fp.exp_avg_sq, self._opt_state), saved):
+                dst.copy_(src)
+            gs["graph"] = graph
+            self._graphs[key] = gs
+        if host_batch and not alias_inputs:
+            gs["t"].copy_(t_b), gs["W"].copy_(W_b)
+        gs["graph"].replay()
+        loss_out.copy_(gs["loss"])
+        return gs["X"], gs["Y"]
 
     def training_step(self, t_b, W_b, loss_out, want_X=False, iteration=0):
         """One training iteration, enqueued on the current stream without synchronising.  (t_b, W_b) are the
@@ -481,7 +525,7 @@ class FBSNN(ABC):
             chol = self._chol_device()
         Xi = self.Xi.detach().reshape(-1, self.D)
         xi_loc = Xi if Xi.shape[0] == 1 else Xi[lo:hi].contiguous()
-        seed = (self.seed + 0x9E3779B97F4A7C15 * self._n_train_calls) & 0xFFFFFFFFFFFFFFFF
+        seed = self.seed & 0xFFFFFFFFFFFFFFFF
         if not dp:
             rc = lib.fbsnn_train_step(ctypes.byref(sp), ctypes.byref(self._hp), _ptr(fp.flat), _ptr(fp.grad),
                                       _ptr(fp.exp_avg), _ptr(fp.exp_avg_sq), _ptr(self._opt_state), _ptr(t_b),

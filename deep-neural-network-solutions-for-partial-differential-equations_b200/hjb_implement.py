@@ -1,4 +1,5 @@
 """Names of the reference's hjb_implement.py hot-path classes."""
+from .drivers import PredictionGenerator, TrainingPhases
 from .fbsnn import FBSNN
 from .networks import Naisnet, Sine
 from .problems import BasketCallOption as _BasketCallOption
@@ -9,4 +10,4 @@ class CallOption(_BasketCallOption):
     """hjb_implement.py:543-586 -- same callables as the with_corr variant, Mm-style N-schedule (:403-406)."""
     _schedule_kind = "mm"
 
-__all__ = ["Sine", "Naisnet", "FBSNN", "CallOption", "HamiltonJacobiBellman"]
+__all__ = ["TrainingPhases", "PredictionGenerator", "Sine", "Naisnet", "FBSNN", "CallOption", "HamiltonJacobiBellman"]

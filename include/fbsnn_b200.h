@@ -114,8 +114,9 @@ int fbsnn_loss_grad(const FbsnnSpec* spec, const float* params, float* grads, co
 /* clip_grad_norm_ + Adam.step on the flat buffers (with_corr_high_dimension_pde.py:424-425).  `opt_state` is
  * FBSNN_OPT_STATE_BYTES of device memory: int64 step counter at byte 0 (zero-initialised by the caller when the
  * optimizer is created -- the reference builds a fresh Adam per train() call, DeepBSDE.py:272), then float
- * clip_coef @8, step_size @12, sqrt(bias_correction2) @16, grad_norm @20, and reduction scratch from byte 64.
- * The step counter is advanced on the device, so the call can be replayed from a CUDA graph. */
+ * clip_coef @8, step_size @12, sqrt(bias_correction2) @16, grad_norm @20, int64 Philox iteration counter @24 (keep it
+ * across optimisers: fbsnn_train_step adds it to `iteration`), and reduction scratch from byte 64.
+ * Both counters are advanced on the device, so the call can be replayed from a CUDA graph. */
 #define FBSNN_OPT_STATE_BYTES 2048
 int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads, float* exp_avg,
                     float* exp_avg_sq, int64_t n_params, void* opt_state, void* stream);

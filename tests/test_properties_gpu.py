@@ -126,6 +126,33 @@ def test_predict_broadcasts_like_the_reference():
         sol.loss_function(t[:, :4], W[:, :4], sol.Xi)                            # N mismatch
 
 
+def test_two_phase_trainer_and_prediction_sampler():
+    """The reference's executor-level callers of the hot path (with_corr...:619-660, :704-726)."""
+    import contextlib, io
+    import dnnpde_b200 as pde
+    from dnnpde_b200.with_corr_high_dimension_pde import CallOption, PredictionGenerator, TrainingPhases
+    torch.manual_seed(4)
+    np.random.seed(4)
+    D6, M6, N6 = 6, 32, 8
+    Xi = np.ones((1, D6))
+    model = CallOption(Xi, 1.0, M6, N6, D6, None, [D6 + 1, 64, 64, 64, 1], "Naisnet", "Sine", "random_correlation")
+    phases = TrainingPhases(model)
+    with contextlib.redirect_stdout(io.StringIO()):
+        graph, min_loss, state, logs = phases.train_initial_phase(30, 1e-3, "Adam")
+        graph2, min_loss2, state2, _ = phases.fine_tuning_phase(10, 1e-5)
+    assert graph.shape[0] == 2 and np.isfinite(min_loss) and state[0].shape == (M6, N6 + 1, D6)
+    assert phases.min_loss == min_loss2 and model.iteration[0] == 0
+    t_test, W_test, X_pred, Y_pred = PredictionGenerator(model, Xi, 5).generate_predictions()
+    assert t_test.shape == (5 * M6, N6 + 1, 1) and X_pred.shape == (5 * M6, N6 + 1, D6) and Y_pred.shape == (5 * M6, N6 + 1, 1)
+    assert W_test.shape == (M6, N6 + 1, D6) and model.M == M6
+    # the batched forward equals the per-sample loop of the reference on the same NumPy stream
+    np.random.seed(42)
+    t0, W0 = model.fetch_minibatch()
+    X0, Y0 = model.predict(Xi, t0, W0)
+    assert np.allclose(Y_pred[:M6], Y0.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert np.allclose(X_pred[:M6], X0.cpu().numpy())
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Monte-Carlo pricer
 # ---------------------------------------------------------------------------------------------------------------

@@ -246,13 +246,22 @@ def measure_roofline(c, args, sol, batches, ms_per_step, m_loc):
     import ctypes
     pk = peaks()
     loss = torch.zeros(1, device=c.dev)
+    nrep = 3                                        # a few consecutive eager steps, every dense launch timed
     c.lib.fbsnn_dense_timing(1)
-    sol.training_step(*batches[0], loss)
+    for i in range(nrep):
+        sol.training_step(*batches[i % len(batches)], loss)
     torch.cuda.synchronize()
     out = (ctypes.c_double * 8)()
     c.pde._lib.check(c.lib.fbsnn_dense_timing_read(out), "timing")
     c.lib.fbsnn_dense_timing(0)
-    n_dense, dense_ms, dense_flops, dense_bytes = int(out[0]), out[1], out[2], out[6]
+    n_dense, dense_ms, dense_flops, dense_bytes = int(out[0]) // nrep, out[1] / nrep, out[2] / nrep, out[6] / nrep
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram bytes per dense launch from the ncu --set full capture
+    if os.path.exists(tf):
+        with open(tf) as f:
+            tj = json.load(f)
+        key = f"{args.precision}_M{args.paths // c.world}"
+        traffic = tj.get(key, {}).get("dram_bytes_per_dense_launch")
     tflops = dense_flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
     gbs = dense_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
     tf32_peak = pk["bf16"] * 0.5          # kind::tf32 issues at half the bf16 rate (nominal 1.1 vs 2.25 PFLOP/s)
@@ -262,12 +271,12 @@ def measure_roofline(c, args, sol, batches, ms_per_step, m_loc):
     # fp32 variant is FMA-issue bound; it is reported against the same HBM peak for comparability, with the FLOP
     # rates alongside ("Roofline").
     return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-            "traffic": None,
+            "traffic": traffic, "algorithmic_bytes_per_launch": dense_bytes / max(n_dense, 1),
             "kernel": (f"gemm_tc_kernel (tcgen05 kind::tf32{' x3 hi/lo split' if args.precision == 'tf32x3' else ''}, "
                        "TMA, TMEM)") if is_tc else "gemm_simt_kernel (fp32 FMA)",
             "launches_per_step": n_dense, "dense_ms_per_step": dense_ms, "dense_share_of_step": dense_ms / ms_per_step,
             "algorithmic_bytes_per_step": dense_bytes, "tflops": tflops, "tf32_peak_tflops": tf32_peak,
-            "tensor_frac": tflops / tf32_peak, "tc_launches": int(out[3]),
+            "tensor_frac": tflops / tf32_peak, "tc_launches": int(out[3]) // nrep,
             "peak_source": f"{pk['source']}: HBM copy {pk['hbm']} GB/s; bf16 {pk['bf16']} TFLOP/s x 0.5 for tf32",
             "step_tflops": FLOP_PER_ROW * m_loc * (NSTEPS + 1) / (ms_per_step * 1e-3) / 1e12}
 

@@ -105,8 +105,9 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   p.rows = rows;
   p.H[0] = p.d_in;
   for (int l = 1; l <= p.L; ++l) p.H[l] = s->width[l - 1];
-  p.loss_blocks = (int)((rows + 7) / 8);
-  p.col_blocks = (int)std::min<long long>(std::max<long long>((rows + 63) / 64, 1), 1024);
+  // loss kernels: 8 warps (= 8 rows at a time) per block, grid-stride; few enough partials for a one-block final sum
+  p.loss_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)num_sms() * 16);
+  p.col_blocks = (int)std::min<long long>(std::max<long long>((rows + 63) / 64, 1), (long long)num_sms() * 2);
   p.col_rows_per_block = (int)((rows + p.col_blocks - 1) / p.col_blocks);
   p.col_blocks = (int)((rows + p.col_rows_per_block - 1) / p.col_rows_per_block);
   // split-K of the weight-gradient contraction: the SIMT kernel wants many CTAs; the persistent tcgen05 kernel

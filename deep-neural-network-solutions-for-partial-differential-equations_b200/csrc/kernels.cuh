@@ -93,6 +93,7 @@ __global__ void path_advance_kernel(const ProblemK p, const PathArgs a) {
   const long long row0 = m * (N + 1);
   float tn = a.t ? a.t[row0] : 0.f;
   float wn = a.W ? a.W[row0 * D + d] : 0.f;
+#pragma unroll 4
   for (int n = 0; n <= N; ++n) {
     const long long r = row0 + n;
     float* xr = a.xin + r * ldx;
@@ -103,15 +104,15 @@ __global__ void path_advance_kernel(const ProblemK p, const PathArgs a) {
     }
     if (a.X_out) a.X_out[r * D + d] = x;
     if (n == N) break;
-    const float tn1 = a.t ? a.t[r + 1] : (float)((double)(n + 1) * (double)a.T / (double)N);
+    const float tn1 = a.t ? __ldg(a.t + r + 1) : (float)((double)(n + 1) * (double)a.T / (double)N);
     const float dt = __fsub_rn(tn1, tn);
     float dw;
     if (a.W) {
-      const float wn1 = a.W[(r + 1) * D + d];
+      const float wn1 = __ldg(a.W + (r + 1) * D + d);   // read-only path: lets the unrolled loop hoist the loads
       dw = __fsub_rn(wn1, wn);
       wn = wn1;
     } else {
-      dw = a.inc[(r + 1) * a.ldi + d];
+      dw = __ldg(a.inc + (r + 1) * a.ldi + d);
     }
     const float sig = p.sigma_kind == FBSNN_SIGMA_PROP ? __fmul_rn(p.sigma_c, x) : p.sigma_c;
     const float sd = __fmul_rn(sig, dw);
@@ -205,10 +206,10 @@ __device__ __forceinline__ void terminal_g(const ProblemK& p, float sumx, float 
 
 __global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
   __shared__ float red[32];
-  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   float contrib = 0.f;
-  if (r < a.rows) {
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < a.rows; r += wstride) {
     const int n = (int)(r % (p.N + 1));
     const float* x = a.xin + r * p.ldx + 1;
     const float* z = a.zf + r * p.ldx + 1;
@@ -229,7 +230,7 @@ __global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
       else if (p.phi_kind == FBSNN_PHI_RY) phi = p.phi_c * y;
       else phi = z2;
       const float e = a.Y[r + 1] - (y + phi * dt + zs);
-      if (lane == 0) { a.ev[r] = e; contrib = e * e; }
+      if (lane == 0) { a.ev[r] = e; contrib += e * e; }
     } else {
       float sx = 0.f, sx2 = 0.f;
       for (int d = lane; d < p.D; d += 32) { const float xv = x[d]; sx += xv; sx2 = fmaf(xv, xv, sx2); }
@@ -244,7 +245,7 @@ __global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
       }
       zt = warp_sum(zt);
       const float e = a.Y[r] - g;
-      if (lane == 0) { a.ev[r] = e; contrib = e * e + zt; }
+      if (lane == 0) { a.ev[r] = e; contrib += e * e + zt; }
     }
   }
   const float tot = block_sum(contrib, red);
@@ -254,10 +255,11 @@ __global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
 // Seeds of the reverse sweeps: ybar = dL/dY, V = [0, dL/dZ, 0-pad] per row.
 __global__ void loss_seed_kernel(const ProblemK p, const LossArgs a) {
   __shared__ float red[32];
-  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  float yb = 0.f;
-  if (r < a.rows) {
+  float ybsum = 0.f;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < a.rows; r += wstride) {
+    float yb = 0.f;
     const int n = (int)(r % (p.N + 1));
     const float* x = a.xin + r * p.ldx + 1;
     const float* z = a.zf + r * p.ldx + 1;
@@ -290,9 +292,10 @@ __global__ void loss_seed_kernel(const ProblemK p, const LossArgs a) {
       v[0] = 0.f;
       for (int c = p.D + 1; c < p.ldx; ++c) v[c] = 0.f;
       a.ybar[r] = yb;
+      ybsum += yb;
     }
   }
-  const float tot = block_sum(lane == 0 ? yb : 0.f, red);
+  const float tot = block_sum(lane == 0 ? ybsum : 0.f, red);
   if (threadIdx.x == 0) a.part[gridDim.x + blockIdx.x] = tot;
 }
 

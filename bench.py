@@ -198,7 +198,7 @@ def make_solver(c, args, batches=None):
     M = args.paths
     torch.manual_seed(1234)
     sol = pde.BlackScholesBarenblatt(xi_bsb(), 1.0, M, NSTEPS, D, LAYERS, "FC", "Sine", precision=args.precision,
-                                     data_parallel=True)
+                                     data_parallel=True, collective=args.collective)
     lo, hi = c.parallel.shard_range(M, c.rank, c.world)
     m_loc = hi - lo
     sp = sol._spec()
@@ -366,6 +366,9 @@ def run_ours(args):
                   "fp32": "f32"}[args.precision],
         "config": workload_config(args), "clocks": clk, "gpu_launches": launches, "final_loss": final_loss,
     }
+    if c.world > 1:
+        line["collective"] = ("fbsnn_peer_allreduce_adam (P2P loads over NVLink, fused with clip norm + Adam)"
+                              if sol.collective == "peer" else "NCCL all-reduce of [grad | loss]")
     line["roofline"] = measure_roofline(c, args, sol, batches, ms_per_step, m_loc)
     if not args.skip_e2e:
         line["e2e"] = measure_e2e(c, args, sol, batches)
@@ -424,6 +427,8 @@ def main():
     ap.add_argument("--cpu-sample-paths", type=int, default=256)
     ap.add_argument("--skip-mc", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU gradient all-reduce: fused NVLink peer-memory kernel (default) or NCCL")
     ap.add_argument("--skip-fp32", action="store_true", help="do not also time the fp32 SIMT variant")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (the JSON line then has no e2e)")
     args = ap.parse_args()

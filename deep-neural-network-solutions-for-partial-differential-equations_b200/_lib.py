@@ -81,6 +81,13 @@ def _declare(lib):
                                     i64, u64, u64, f32p, vp, sz, f32p, f32p, f32p, f32p, vp]
     lib.fbsnn_adam_step.restype = c.c_int
     lib.fbsnn_adam_step.argtypes = [c.POINTER(S.FbsnnAdam), f32p, f32p, f32p, f32p, i64, vp, vp]
+    lib.fbsnn_peer_allreduce_adam.restype = c.c_int
+    lib.fbsnn_peer_allreduce_adam.argtypes = [c.POINTER(S.FbsnnAdam), f32p, vp, c.c_int, c.c_int, f32p, f32p, f32p,
+                                              i64, vp, vp]
+    lib.fbsnn_peer_buffer_floats.restype = c.c_int
+    lib.fbsnn_peer_buffer_floats.argtypes = [i64, c.POINTER(i64), c.POINTER(i64)]
+    lib.fbsnn_peer_wait.restype = c.c_int
+    lib.fbsnn_peer_wait.argtypes = [f32p, i64, c.c_int, vp, vp]
     lib.fbsnn_train_step.restype = c.c_int
     lib.fbsnn_train_step.argtypes = [c.POINTER(S.FbsnnSpec), c.POINTER(S.FbsnnAdam), f32p, f32p, f32p, f32p, vp,
                                      f32p, f32p, f32p, i64, i64, c.c_float, i64, u64, u64, f32p, vp, sz, f32p,
@@ -97,7 +104,8 @@ def _declare(lib):
 
 EXPORTS = ["fbsnn_last_error", "fbsnn_version", "fbsnn_launch_count", "fbsnn_dense_timing",
            "fbsnn_dense_timing_read", "fbsnn_debug_gemm", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
-           "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_adam_step", "fbsnn_train_step", "mc_scratch_bytes", "mc_launch_count",
+           "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_adam_step", "fbsnn_peer_buffer_floats", "fbsnn_peer_wait",
+           "fbsnn_peer_allreduce_adam", "fbsnn_train_step", "mc_scratch_bytes", "mc_launch_count",
            "mc_basket_price", "mc_generate_paths"]
 
 

@@ -623,10 +623,12 @@ static int loss_grad_impl(const FbsnnSpec* s, const float* params, float* grads,
 }
 
 static int adam_impl(const FbsnnAdam* hp, float* params, const float* grads, float* m, float* v, int64_t n,
-                     void* opt_state, float* gsq_part, int gsq_blocks, cudaStream_t st) {
+                     void* opt_state, float* gsq_part, int gsq_blocks, cudaStream_t st, bool have_gradsq = false) {
   if (!hp || !params || !grads || !m || !v || !opt_state || n < 1) return fail(FBSNN_E_BADARG, "adam: null argument");
-  gradsq_kernel<<<gsq_blocks, 256, 0, st>>>(grads, n, gsq_part);
-  LAUNCH_CHECK("gradsq");
+  if (!have_gradsq) {
+    gradsq_kernel<<<gsq_blocks, 256, 0, st>>>(grads, n, gsq_part);
+    LAUNCH_CHECK("gradsq");
+  }
   opt_prepare_kernel<<<1, 256, 0, st>>>(gsq_part, gsq_blocks, *hp, (OptState*)opt_state);
   LAUNCH_CHECK("opt_prepare");
   const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
@@ -768,6 +770,45 @@ int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads,
   // scratch for the squared-norm partials lives behind the 64-byte state block (FBSNN_OPT_STATE_BYTES)
   return adam_impl(host_hp, params, grads, exp_avg, exp_avg_sq, n_params, opt_state,
                    (float*)((char*)opt_state + 64), 256, (cudaStream_t)stream);
+}
+
+int fbsnn_peer_buffer_floats(int64_t n_params, int64_t* flag_offset_out, int64_t* total_out) {
+  if (n_params < 1 || n_params % 4 || !flag_offset_out || !total_out) return fail(FBSNN_E_BADARG, "peer buffer: n_params must be a positive multiple of 4");
+  const int64_t fo = (n_params + 4 + 63) / 64 * 64;
+  *flag_offset_out = fo;
+  *total_out = fo + 2 * kPeerMaxWorld;
+  return 0;
+}
+
+int fbsnn_peer_wait(const float* local_buf, int64_t n_params, int world, const void* opt_state, void* stream) {
+  if (!local_buf || !opt_state || world < 1 || world > kPeerMaxWorld) return fail(FBSNN_E_BADARG, "peer wait: bad argument");
+  int64_t fo, tot;
+  int rc = fbsnn_peer_buffer_floats(n_params, &fo, &tot);
+  if (rc) return rc;
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(local_buf, fo, world, (const OptState*)opt_state);
+  LAUNCH_CHECK("peer_wait");
+  return 0;
+}
+
+int fbsnn_peer_allreduce_adam(const FbsnnAdam* host_hp, float* params, const void* peer_ptrs_dev, int world, int rank,
+                              float* grad_sum, float* exp_avg, float* exp_avg_sq, int64_t n_params, void* opt_state,
+                              void* stream) {
+  if (!peer_ptrs_dev || !grad_sum || !opt_state || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world)
+    return fail(FBSNN_E_BADARG, "peer allreduce: bad argument");
+  int64_t fo, tot;
+  int rc = fbsnn_peer_buffer_floats(n_params, &fo, &tot);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = (float*)((char*)opt_state + 64);
+  PeerArgs a{};
+  a.peers = (float* const*)peer_ptrs_dev, a.world = world, a.rank = rank;
+  a.n4 = n_params / 4 + 1;       // + the float4 that carries the loss
+  a.n_grad = n_params, a.flag_off = fo;
+  a.st = (const OptState*)opt_state;
+  a.counter = (unsigned*)((char*)opt_state + 1536);
+  peer_reduce_kernel<<<256, 256, 0, st>>>(a, grad_sum, part);
+  LAUNCH_CHECK("peer_reduce");
+  return adam_impl(host_hp, params, grad_sum, exp_avg, exp_avg_sq, n_params, opt_state, part, 256, st, true);
 }
 
 int fbsnn_train_step(const FbsnnSpec* spec, const FbsnnAdam* host_hp, float* params, float* grads,

@@ -443,6 +443,101 @@ __global__ void gradsq_kernel(const float* __restrict__ g, long long n, float* _
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
+// ----------------------------------------------------------------------------------------------------
+// Fused gradient all-reduce over NVLink peer memory (multi-GPU training step): ONE kernel does the cross-GPU
+// barrier, the reduction over peer buffers and the squared norm for clip_grad_norm_; Adam follows on the same
+// stream.  Replaces ncclAllReduce + the norm kernel; the payload (0.9 MB) is latency-bound, so one pass of 16-byte
+// P2P loads is the minimum.
+//
+// Every rank's gradient kernels write into a symmetric buffer that all peers have mapped:
+//   floats [0, n_grad) gradient | [n_grad] loss | ... | u32 flags at float offset flag_off: ready[16], done[16]
+// Protocol for epoch e = (Philox iteration counter + 1), identical on all ranks and never reset:
+//   1. block 0 stores e into ready[rank] of every peer (release.sys: this rank's gradient kernels finished
+//      earlier on the stream); every block spins (acquire.sys) until its own ready[0..W) >= e
+//   2. all blocks sum the W buffers in rank order 0..W-1 (so every rank gets bit-identical sums) with L1-bypassing
+//      loads, store locally, accumulate the squared norm
+//   3. the last block to finish stores e into done[rank] of every peer; peer_wait_kernel at the start of the next
+//      iteration spins until done[0..W) >= e before any gradient kernel overwrites the buffer
+// Spins are bounded by a wall-clock limit and trap instead of hanging the GPU.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kPeerMaxWorld = 16;
+constexpr unsigned long long kPeerTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_spin(const unsigned* flag, unsigned epoch) {
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+    if (global_ns() - t0 > kPeerTimeoutNs) {
+      printf("fbsnn peer all-reduce: timed out waiting for a peer flag (have %u, want %u)\n", ld_acquire_sys(flag), epoch);
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ float4 ld4_peer(const float* p) {   // L1 caches peer lines; always go to the owner
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+struct PeerArgs {
+  float* const* peers;       // device array [world]: every rank's symmetric buffer as mapped here
+  int world, rank;
+  long long n4;              // float4 count to reduce (gradient + the float4 carrying the loss)
+  long long n_grad;
+  long long flag_off;        // float offset of the flag block
+  const OptState* st;
+  unsigned* counter;         // local: blocks finished (self-resetting)
+};
+__global__ void peer_reduce_kernel(PeerArgs a, float* __restrict__ out, float* __restrict__ part) {
+  __shared__ float red[32];
+  const unsigned epoch = (unsigned)(a.st->rng_iter + 1);
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned*>(a.peers[threadIdx.x] + a.flag_off) + a.rank, epoch);
+  }
+  if (threadIdx.x < a.world)
+    peer_spin(reinterpret_cast<const unsigned*>(a.peers[a.rank] + a.flag_off) + threadIdx.x, epoch);
+  __syncthreads();
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = ld4_peer(a.peers[0] + 4 * i);
+    for (int r = 1; r < a.world; ++r) {
+      const float4 v = ld4_peer(a.peers[r] + 4 * i);
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = s;
+    if (4 * i < a.n_grad) acc = fmaf(s.x, s.x, fmaf(s.y, s.y, fmaf(s.z, s.z, fmaf(s.w, s.w, acc))));
+  }
+  acc = block_sum(acc, red);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < a.world) {
+    if (threadIdx.x == 0) *a.counter = 0;
+    st_release_sys(reinterpret_cast<unsigned*>(a.peers[threadIdx.x] + a.flag_off) + kPeerMaxWorld + a.rank, epoch);
+  }
+}
+// start of an iteration: every peer has finished reading this rank's buffer in the previous epoch
+__global__ void peer_wait_kernel(const float* local_buf, long long flag_off, int world, const OptState* st) {
+  const unsigned epoch = (unsigned)st->rng_iter;
+  if (epoch != 0 && threadIdx.x < world)
+    peer_spin(reinterpret_cast<const unsigned*>(local_buf + flag_off) + kPeerMaxWorld + threadIdx.x, epoch);
+}
+
 __global__ void opt_prepare_kernel(const float* __restrict__ part, int npart, FbsnnAdam hp, OptState* st) {
   __shared__ double red[32];
   double acc = 0.0;

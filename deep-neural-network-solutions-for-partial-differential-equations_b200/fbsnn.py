@@ -72,7 +72,7 @@ class FBSNN(ABC):
         names_short = ["layers", "mode", "activation"]
         names_long = ["Mm", "layers", "mode", "activation", "correlation_type"]
         extras = {k: kw.pop(k) for k in ("precision", "n_schedule", "brownian", "seed", "device", "data_parallel",
-                                          "cuda_graph") if k in kw}
+                                          "cuda_graph", "collective") if k in kw}
         if len(args) == 3 or (len(args) < 3 and "Mm" not in kw and len(args) + len(kw) == 3):
             vals = dict(zip(names_short, args))
             self._arity = "short"
@@ -135,6 +135,8 @@ class FBSNN(ABC):
         self._n_train_calls = 0
         self._graphs = {}
         self.use_cuda_graph = bool(extras.get("cuda_graph", True))
+        self._peer = None
+        self.collective = extras.get("collective", "peer")   # multi-GPU: "peer" (fused NVLink kernel) | "nccl"
 
     # ------------------------------------------------------------------------------------------------
     # host-side pieces kept verbatim in meaning
@@ -442,7 +444,8 @@ class FBSNN(ABC):
                     self.iteration.append(it)
             self.last_losses = loss_buf[:N_Iter].cpu().numpy()     # device -> host read of the step results
             self.last_Y0 = y0_buf[:N_Iter].cpu().numpy()
-        self._fp.attach_grads()
+        # p.grad = the gradient the last Adam step used (summed over ranks on the multi-GPU peer path)
+        self._fp.attach_grads(self._peer["sum"][:self._fp.n] if self._peer is not None else None)
         graph = np.stack((self.iteration, self.training_loss))
         if self._train_returns == "graph":
             return graph
@@ -534,16 +537,63 @@ class FBSNN(ABC):
                                       self._stream())
             _lib.check(rc, "fbsnn_train_step")
         else:
+            peer = self._peer_buffers() if self.collective == "peer" else None
+            loss_slot = loss_out
+            if peer:
+                # peers have finished reading the previous iteration's gradients from this rank's buffer
+                loss_slot = peer["buf"][fp.n:fp.n + 1]
+                _lib.check(lib.fbsnn_peer_wait(_ptr(peer["buf"]), fp.n, parallel.world_size(), _ptr(self._opt_state),
+                                               self._stream()), "fbsnn_peer_wait")
             rc = lib.fbsnn_loss_grad(ctypes.byref(sp), _ptr(fp.flat), _ptr(fp.grad), _ptr(t_b), _ptr(W_b),
                                      _ptr(xi_loc), xi_loc.shape[0], m_loc, float(self.T), lo, seed, iteration,
-                                     _ptr(chol), _ptr(ws), ws.numel(), _ptr(X), _ptr(Y), None, _ptr(loss_out),
+                                     _ptr(chol), _ptr(ws), ws.numel(), _ptr(X), _ptr(Y), None, _ptr(loss_slot),
                                      self._stream())
             _lib.check(rc, "fbsnn_loss_grad")
-            parallel.allreduce_grads_and_loss(fp.grad, loss_out)
-            rc = lib.fbsnn_adam_step(ctypes.byref(self._hp), _ptr(fp.flat), _ptr(fp.grad), _ptr(fp.exp_avg),
-                                     _ptr(fp.exp_avg_sq), fp.n, _ptr(self._opt_state), self._stream())
-            _lib.check(rc, "fbsnn_adam_step")
+            if peer:
+                # one kernel: cross-GPU barrier + sum of the peers' buffers over NVLink + clip norm; then Adam
+                rc = lib.fbsnn_peer_allreduce_adam(ctypes.byref(self._hp), _ptr(fp.flat),
+                                                   ctypes.c_void_p(peer["ptrs"]), parallel.world_size(), parallel.rank(),
+                                                   _ptr(peer["sum"]), _ptr(fp.exp_avg), _ptr(fp.exp_avg_sq), fp.n,
+                                                   _ptr(self._opt_state), self._stream())
+                _lib.check(rc, "fbsnn_peer_allreduce_adam")
+                loss_out.copy_(peer["sum"][fp.n:fp.n + 1])
+            else:
+                parallel.allreduce_grads_and_loss(fp.grad, loss_out)
+                rc = lib.fbsnn_adam_step(ctypes.byref(self._hp), _ptr(fp.flat), _ptr(fp.grad), _ptr(fp.exp_avg),
+                                         _ptr(fp.exp_avg_sq), fp.n, _ptr(self._opt_state), self._stream())
+                _lib.check(rc, "fbsnn_adam_step")
         return X, Y
+
+    def _peer_buffers(self):
+        """Symmetric (peer-mapped) [gradient | loss | flags] buffer for the fused NVLink all-reduce
+        (fbsnn_peer_allreduce_adam).  torch's symmetric-memory allocator only provides the peer mapping; the
+        barrier and the reduction are this library's kernel.  Falls back to NCCL if the devices cannot map each
+        other's memory."""
+        if self._peer is not None:
+            return self._peer
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            lib = _lib.load()
+            fp = self._fp
+            flag_off, total = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(lib.fbsnn_peer_buffer_floats(fp.n, ctypes.byref(flag_off), ctypes.byref(total)),
+                       "fbsnn_peer_buffer_floats")
+            buf = symm.empty(total.value, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            dist.barrier()                     # every rank has zeroed its flags before anyone can signal
+            self._peer = {"buf": buf, "hdl": hdl, "ptrs": int(hdl.buffer_ptrs_dev),
+                          "sum": torch.zeros(fp.n + 4, device=self.device)}
+            fp.grad = buf[:fp.n]               # the gradient kernels now write straight into the shared buffer
+            fp.attach_grads()
+        except Exception as e:                 # noqa: BLE001 -- e.g. no P2P between the devices
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({e!r}); using the NCCL all-reduce")
+            self.collective = "nccl"
+            self._peer = None
+        return self._peer
 
     def _train_generic(self, N_Iter, learning_rate, optimizer_type):
         """Non-Adam optimisers of the reference's menu (with_corr...:370-389): gradients from the fused kernels,

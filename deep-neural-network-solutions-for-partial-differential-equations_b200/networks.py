@@ -161,11 +161,13 @@ class FlatParams:
     def offset_of(self, p) -> int:
         return self._by_param[id(p)]
 
-    def attach_grads(self):
-        """Point every p.grad at its slice of the flat gradient buffer."""
+    def attach_grads(self, src=None):
+        """Point every p.grad at its slice of the flat gradient buffer (or of `src`, same layout: the reduced
+        gradients of the multi-GPU peer all-reduce)."""
+        buf = self.grad if src is None else src
         for name, p in self.model.named_parameters():
             o = self.offsets[name]
-            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+            p.grad = buf[o:o + p.numel()].view(p.shape)
 
     def grad_views(self):
         return [self.grad[self.offsets[n]:self.offsets[n] + p.numel()].view(p.shape)

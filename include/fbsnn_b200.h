@@ -121,6 +121,24 @@ int fbsnn_loss_grad(const FbsnnSpec* spec, const float* params, float* grads, co
 int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads, float* exp_avg,
                     float* exp_avg_sq, int64_t n_params, void* opt_state, void* stream);
 
+/* Multi-GPU: gradient all-reduce fused with its cross-GPU barrier and the clip norm, then the Adam update, over
+ * NVLink peer memory instead of NCCL (no reference counterpart -- upstream is single-device).
+ * Each rank owns one symmetric buffer of fbsnn_peer_buffer_floats() floats, zero-initialised once and mapped into
+ * every peer: [0, n_params) gradients (pass it as `grads` to fbsnn_loss_grad), [n_params] that rank's loss (pass
+ * as `loss_out`), u32 flags from *flag_offset_out.  `peer_ptrs_dev` = device array of `world` pointers to the
+ * ranks' buffers as mapped in this process, index = rank.
+ * Per iteration:  fbsnn_peer_wait (peers finished reading the previous iteration's gradients)  ->
+ * fbsnn_loss_grad  ->  fbsnn_peer_allreduce_adam.  One kernel signals/waits the peers (release/acquire at system
+ * scope, bounded spin), sums the W buffers in rank order (=> bit-identical parameters on every rank) into
+ * grad_sum (local, n_params + 4 floats; [n_params] = global loss) and accumulates the squared norm; clip + Adam
+ * follow on the same stream.  The epoch is the Philox iteration counter of opt_state (never reset), so all ranks
+ * must have taken the same number of optimiser steps; the sequence is CUDA-graph capturable. */
+int fbsnn_peer_buffer_floats(int64_t n_params, int64_t* flag_offset_out, int64_t* total_out);
+int fbsnn_peer_wait(const float* local_buf, int64_t n_params, int world, const void* opt_state, void* stream);
+int fbsnn_peer_allreduce_adam(const FbsnnAdam* host_hp, float* params, const void* peer_ptrs_dev, int world, int rank,
+                              float* grad_sum, float* exp_avg, float* exp_avg_sq, int64_t n_params, void* opt_state,
+                              void* stream);
+
 /* One fused training iteration on one GPU = fbsnn_loss_grad + fbsnn_adam_step.  Multi-GPU callers run
  * fbsnn_loss_grad, all-reduce [grads | loss] over NCCL, then fbsnn_adam_step. */
 int fbsnn_train_step(const FbsnnSpec* spec, const FbsnnAdam* host_hp, float* params, float* grads,

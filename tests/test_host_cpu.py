@@ -27,6 +27,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.fbsnn_version() == 100
 
 
+def test_peer_buffer_layout_without_gpu():
+    """Symmetric [gradient | loss | flags] buffer of the fused NVLink all-reduce (host-side layout arithmetic)."""
+    lib = pde._lib.load()
+    fo, tot = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.fbsnn_peer_buffer_floats(223744, ctypes.byref(fo), ctypes.byref(tot)) == 0
+    assert fo.value >= 223744 + 4 and fo.value % 64 == 0 and tot.value == fo.value + 32   # ready[16] + done[16]
+    assert lib.fbsnn_peer_buffer_floats(223745, ctypes.byref(fo), ctypes.byref(tot)) == -1     # not a multiple of 4
+    assert lib.fbsnn_peer_allreduce_adam(None, None, None, 2, 0, None, None, None, 8, None, None) == -1
+    assert lib.fbsnn_peer_wait(None, 8, 2, None, None) == -1
+
+
 def test_workspace_and_validation_without_gpu():
     lib = pde._lib.load()
     sol = pde.BlackScholesBarenblatt(gu.make_xi("bsb", 100), 1.0, 100, 50, 100, [101] + 4 * [256] + [1], "FC", "Sine")

@@ -5,18 +5,19 @@ The directory name is not a Python identifier; import it with
 or through the `dnnpde_b200` alias module at the repository root.
 """
 from . import _lib, parallel, spec
+from . import basket_pricer
 from .drivers import PredictionGenerator, TrainingPhases
 from .fbsnn import FBSNN
 from .mc_pricer import (AnalyticalBlackScholes, BasketOption, BlackScholesModel, CorrelationMatrix,
                         MonteCarloPricer)
 from .networks import Naisnet, Sine
 from .problems import (BasketCallOption, BlackScholesBarenblatt, BSPDETestCase, CallOption1D, CallOptionND,
-                       HamiltonJacobiBellman, u_exact)
+                       HamiltonJacobiBellman, hjb_u_exact, u_exact)
 
 build = _lib.build
 
 __all__ = ["FBSNN", "Sine", "Naisnet", "BlackScholesBarenblatt", "BasketCallOption", "BSPDETestCase",
-           "CallOption1D", "CallOptionND", "HamiltonJacobiBellman", "u_exact", "CorrelationMatrix",
+           "CallOption1D", "CallOptionND", "HamiltonJacobiBellman", "u_exact", "hjb_u_exact", "basket_pricer", "CorrelationMatrix",
            "BlackScholesModel", "BasketOption", "MonteCarloPricer", "AnalyticalBlackScholes", "build",
            "TrainingPhases", "PredictionGenerator",
            "parallel", "spec"]

@@ -64,6 +64,8 @@ def _declare(lib):
     lib.fbsnn_dense_timing.argtypes = [c.c_int]
     lib.fbsnn_dense_timing_read.restype = c.c_int
     lib.fbsnn_dense_timing_read.argtypes = [c.POINTER(c.c_double)]
+    lib.fbsnn_dense_timing_entry.restype = c.c_char_p
+    lib.fbsnn_dense_timing_entry.argtypes = [c.c_int, c.POINTER(c.c_double)]
     lib.fbsnn_debug_gemm.restype = c.c_int
     lib.fbsnn_debug_gemm.argtypes = [c.c_int] * 6 + [f32p, c.c_int, f32p, c.c_int, f32p, c.c_int, vp]
     lib.fbsnn_workspace_bytes.restype = c.c_int
@@ -98,15 +100,19 @@ def _declare(lib):
     lib.mc_scratch_bytes.argtypes = []
     lib.mc_basket_price.restype = c.c_int
     lib.mc_basket_price.argtypes = [c.POINTER(S.McSpec), f32p, f32p, f32p, u64, u64, u64, vp, vp, vp]
+    lib.mc_basket_price_delta.restype = c.c_int
+    lib.mc_basket_price_delta.argtypes = [c.POINTER(S.McSpec), f32p, f32p, f32p, u64, u64, u64, vp, vp, vp, vp]
+    lib.mc_hjb_exact.restype = c.c_int
+    lib.mc_hjb_exact.argtypes = [c.c_int32, c.c_int32, f32p, f32p, c.c_float, u64, u64, vp, vp, vp]
     lib.mc_generate_paths.restype = c.c_int
     lib.mc_generate_paths.argtypes = [c.POINTER(S.McSpec), f32p, f32p, u64, u64, u64, f32p, vp]
 
 
 EXPORTS = ["fbsnn_last_error", "fbsnn_version", "fbsnn_launch_count", "fbsnn_dense_timing",
-           "fbsnn_dense_timing_read", "fbsnn_debug_gemm", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
+           "fbsnn_dense_timing_read", "fbsnn_dense_timing_entry", "fbsnn_debug_gemm", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
            "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_adam_step", "fbsnn_peer_buffer_floats", "fbsnn_peer_wait",
            "fbsnn_peer_allreduce_adam", "fbsnn_train_step", "mc_scratch_bytes", "mc_launch_count",
-           "mc_basket_price", "mc_generate_paths"]
+           "mc_basket_price", "mc_basket_price_delta", "mc_hjb_exact", "mc_generate_paths"]
 
 
 def load():

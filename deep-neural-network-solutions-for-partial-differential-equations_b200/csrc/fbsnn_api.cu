@@ -196,6 +196,7 @@ static int g_ntimed = 0;
 static cudaEvent_t g_ev0[kMaxTimed], g_ev1[kMaxTimed];
 static double g_flops[kMaxTimed], g_bytes[kMaxTimed];
 static bool g_timed_tc[kMaxTimed];
+static const char* g_timed_what[kMaxTimed];
 
 // 3xTF32: weight matrices that have exact-TF32 hi/lo twins in the workspace (filled by split_weights())
 struct SplitW {
@@ -231,6 +232,7 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
     // algorithmic HBM bytes: both operands once + every row array the fused epilogue reads or writes
     g_bytes[slot] = 4.0 * (k * ((double)g.M + (double)g.N) + (double)g.M * (double)g.N * epi.io_arrays() * nsplit);
     g_timed_tc[slot] = tc;
+    g_timed_what[slot] = what;
     cudaEventRecord(g_ev0[slot], st);
   }
   ++g_launches;
@@ -660,6 +662,16 @@ int fbsnn_dense_timing_read(double* out8) {
     if (g_timed_tc[i]) out8[3] += 1, out8[4] += ms, out8[5] += g_flops[i], out8[7] += g_bytes[i];
   }
   return 0;
+}
+
+// One recorded dense launch (caller has synchronised): out4 = {ms, algorithmic FLOPs, algorithmic bytes, 1 if tcgen05};
+// returns the sweep tag ("F", "A", "Du", "T", "B", "G", ...) or NULL when i is out of range.
+const char* fbsnn_dense_timing_entry(int i, double* out4) {
+  if (i < 0 || i >= g_ntimed || !out4) return nullptr;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, g_ev0[i], g_ev1[i]) != cudaSuccess) return nullptr;
+  out4[0] = ms, out4[1] = g_flops[i], out4[2] = g_bytes[i], out4[3] = g_timed_tc[i] ? 1.0 : 0.0;
+  return g_timed_what[i];
 }
 
 // Test hook: one dense GEMM C = A * B with a plain store epilogue, on the SIMT or the tcgen05 kernel.

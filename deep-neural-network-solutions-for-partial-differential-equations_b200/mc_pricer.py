@@ -146,6 +146,45 @@ class MonteCarloPricer:
             raise RuntimeError(f"mc_basket_price failed ({rc}); D must be <= 256")
         return sums
 
+    def price_and_delta(self, S0, return_stderr: bool = False):
+        """Price and the D pathwise deltas d price / d S0_d from ONE fused simulation pass
+        (mc_basket_price_delta): the quantity basket_pricer.py:68-81 estimates by bump-and-revalue."""
+        dev = _device(self.device)
+        lib = _lib.load()
+        m = self.model
+        n_total = int(self.num_simulations)
+        seed = _draw_seed(self.seed)
+        self.last_seed = seed
+        if self.data_parallel and parallel.is_distributed():
+            lo, hi = parallel.shard_range(n_total, parallel.rank(), parallel.world_size())
+        else:
+            lo, hi = 0, n_total
+        D = m.dimensions
+        out = torch.zeros(2 + D, dtype=torch.float64, device=dev)
+        if hi > lo:
+            sp = m._mc_spec(self.T, self.N, self.option.strike)
+            S0d = torch.as_tensor(np.broadcast_to(np.asarray(S0, dtype=np.float32), (D,)).copy()).to(dev)
+            wd = torch.as_tensor(np.broadcast_to(np.asarray(self.option.weights, dtype=np.float32), (D,)).copy()).to(dev)
+            cT = m._chol_T(dev)
+            scratch = torch.empty(lib.mc_scratch_bytes(), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.mc_basket_price_delta(ctypes.byref(sp), ctypes.c_void_p(S0d.data_ptr()),
+                                               ctypes.c_void_p(wd.data_ptr()),
+                                               None if cT is None else ctypes.c_void_p(cT.data_ptr()), hi - lo, seed, lo,
+                                               ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                               ctypes.c_void_p(out[2:].data_ptr()),
+                                               ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"mc_basket_price_delta failed ({rc}); D must be <= 256")
+        if self.data_parallel:
+            parallel.allreduce_sums(out)
+        vals = out.cpu().numpy()
+        mean = float(vals[0]) / n_total
+        var = max(float(vals[1]) / n_total - mean * mean, 0.0)
+        self.last_stderr = math.sqrt(var / n_total)
+        deltas = vals[2:] / n_total
+        return (mean, deltas, self.last_stderr) if return_stderr else (mean, deltas)
+
     def price(self, S0, return_stderr: bool = False):
         """exp(-rT) * mean payoff (:88-93).  `return_stderr=True` also returns the standard error, which the
         reference does not compute."""

@@ -45,6 +45,32 @@ def u_exact(t, X, T=1.0, r=0.05, sigma_max=0.4):
     return np.exp((r + sigma_max ** 2) * (T - t)) * np.sum(X ** 2, 1, keepdims=True)
 
 
+def hjb_u_exact(t, X, T=1.0, MC=10 ** 5, seed=None, device=None):
+    """Cole-Hopf Monte-Carlo "exact" solution the HJB driver plots against (hjb_implement.py:1085-1094):
+    t (NC, 1), X (NC, D) -> (NC, 1) float64 NumPy, `MC` Philox draws per time point on the device (mc_hjb_exact).
+    The seed comes from the NumPy global RNG unless given, so np.random.seed(s) keeps runs reproducible."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _lib
+    from .mc_pricer import _device, _draw_seed
+    dev = _device(device)
+    lib = _lib.load()
+    td = torch.as_tensor(np.asarray(t, dtype=np.float32)).reshape(-1).contiguous().to(dev)
+    Xd = torch.as_tensor(np.asarray(X, dtype=np.float32)).reshape(td.numel(), -1).contiguous().to(dev)
+    out = torch.empty(td.numel(), dtype=torch.float64, device=dev)
+    scratch = torch.empty(lib.mc_scratch_bytes(), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mc_hjb_exact(Xd.shape[1], td.numel(), ctypes.c_void_p(td.data_ptr()), ctypes.c_void_p(Xd.data_ptr()),
+                              float(T), int(MC), _draw_seed(seed), ctypes.c_void_p(scratch.data_ptr()),
+                              ctypes.c_void_p(out.data_ptr()),
+                              ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"mc_hjb_exact failed ({rc})")
+    return out.cpu().numpy().reshape(-1, 1)
+
+
 class BasketCallOption(FBSNN):
     """Basket-mean call, `CallOption` of with_corr_high_dimension_pde.py:546-596 and hjb_implement.py:543-586.
     phi keeps the upstream form r*Y (the avg_XZ term is computed and discarded there)."""

@@ -72,6 +72,7 @@ int fbsnn_version(void);
 long long fbsnn_launch_count(void);
 void fbsnn_dense_timing(int enable);
 int fbsnn_dense_timing_read(double* out8);
+const char* fbsnn_dense_timing_entry(int i, double* out4);   /* one recorded launch: {ms, FLOPs, bytes, is tcgen05}; returns its sweep tag */
 
 /* Test hook (tests/test_gemm_gpu.py): one dense GEMM with a plain store on the SIMT (use_tc = 0), tcgen05 TF32
  * (use_tc = 1) or tcgen05 3xTF32 (use_tc = 2) kernel.
@@ -162,6 +163,20 @@ long long mc_launch_count(void);   /* kernels launched by the pricer since load 
 int mc_basket_price(const McSpec* spec, const float* S0, const float* weights, const float* chol_T,
                     uint64_t n_paths, uint64_t seed, uint64_t path_offset, void* scratch, double* sums_out,
                     void* stream);
+
+/* As mc_basket_price, plus the pathwise deltas: delta_sums_out[d] = sum over paths of
+ * disc * 1{basket > K} * w_d * S_T,d / S0_d  (double, D entries; divide by the global path count).  This is the
+ * quantity basket_pricer.py:68-81 (BasketOptionPricer.delta) estimates by bump-and-revalue with fresh noise per
+ * bump; the pathwise form is unbiased and costs one pass. */
+int mc_basket_price_delta(const McSpec* spec, const float* S0, const float* weights, const float* chol_T,
+                          uint64_t n_paths, uint64_t seed, uint64_t path_offset, void* scratch, double* sums_out,
+                          double* delta_sums_out, void* stream);
+
+/* Replaces the Cole-Hopf Monte-Carlo "exact" solution of the HJB driver (hjb_implement.py:1088-1094):
+ * u_out[n] = -ln mean_{i < n_mc} 1 / (0.5 + 0.5 |X[n,:] + sqrt(2 |T - t[n]|) W_i|^2), W_i ~ N(0, I_D) from Philox
+ * keyed by (seed, i, n).  t (n_times), X (n_times, D) device fp32; u_out (n_times) device double. */
+int mc_hjb_exact(int32_t D, int32_t n_times, const float* t, const float* X, float T, uint64_t n_mc, uint64_t seed,
+                 void* scratch, double* u_out, void* stream);
 
 /* Replaces BlackScholesModel.generate_paths (:49-67): paths_out (n_paths, N+1, D) float32. */
 int mc_generate_paths(const McSpec* spec, const float* S0, const float* chol_T, uint64_t n_paths,

@@ -221,6 +221,23 @@ def run_mc_cases():
     np.savez_compressed(os.path.join(OUT, "mc_pricer.npz"), **out)
 
 
+def run_basket_pricer_case():
+    """basket_pricer.py: MonteCarloSimulator.simulate + BasketOptionPricer.price under a fixed NumPy seed."""
+    sys.modules.setdefault("sklearn", MagicMock()), sys.modules.setdefault("sklearn.decomposition", MagicMock())
+    mod = load_reference("basket_pricer.py")
+    S0 = np.linspace(0.9, 1.1, 5)
+    corr = np.full((5, 5), 0.25) + 0.75 * np.eye(5)
+    np.random.seed(12)
+    sim = mod.MonteCarloSimulator(S0, 0.05, 0.2, 1.0, 0.1, corr.copy())
+    paths = sim.simulate(3000)
+    price = mod.BasketOptionPricer(1.0, 1.0, corr.copy()).price(paths, 0.05)
+    np.savez_compressed(os.path.join(OUT, "basket_pricer.npz"), S0=S0, corr=corr, price=np.float64(price),
+                        paths_shape=np.array(paths.shape), paths_sum=np.float64(paths.sum()),
+                        paths_terminal_head=paths[:, -1, :8],
+                        cfg=np.array(json.dumps(dict(seed=12, r=0.05, sigma=0.2, T=1.0, dt=0.1, n=3000, strike=1.0))))
+    print(f"basket_pricer: price={price:.6f} shape={paths.shape}")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("make_golden.py needs /root/reference (build container only)")
@@ -234,3 +251,5 @@ if __name__ == "__main__":
         run_train_api_case()
     if not only or "mc" in only:
         run_mc_cases()
+    if not only or "basket_pricer" in only:
+        run_basket_pricer_case()

@@ -72,3 +72,45 @@ def terminal_moments(S0, rate, sigma, corr, weights, T):
     mean = f.sum()
     cov = np.outer(f, f) * (np.exp(sigma ** 2 * T * corr) - 1.0)
     return float(mean), float(cov.sum())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# basket_pricer.py (MonteCarloSimulator :7-53, BasketOptionPricer :56-86) and the HJB Cole-Hopf comparator
+# (hjb_implement.py:1085-1094) -- SURVEY.md section 8f rows 3-4
+# ------------------------------------------------------------------------------------------------------------
+def simulate_asset_paths(S0, r, sigma, T, dt, corr, num_simulations):
+    """basket_pricer.py:41-53: (num_assets, num_steps+1, num_simulations) via one np.random.normal draw,
+    tensordot with the Cholesky factor and a cumulative product."""
+    S0 = np.asarray(S0, dtype=np.float64)
+    n_assets, n_steps = len(S0), int(T / dt)
+    L = np.linalg.cholesky(corr) if corr is not None else np.eye(n_assets)
+    Z = np.random.normal(size=(n_assets, n_steps, num_simulations))
+    cz = np.tensordot(L, Z, axes=(1, 0))
+    inc = np.exp((r - 0.5 * sigma ** 2) * dt + sigma * np.sqrt(dt) * cz)
+    return np.cumprod(np.insert(inc, 0, S0[:, np.newaxis], axis=1), axis=1)
+
+
+def mean_basket_price(asset_paths, r, strike, T):
+    """basket_pricer.py:62-66: equal-weight basket (np.mean over assets), terminal payoff, discounted mean."""
+    avg = np.mean(asset_paths, axis=0)
+    return float(np.exp(-r * T) * np.mean(np.maximum(avg[-1, :] - strike, 0)))
+
+
+def pathwise_deltas(asset_paths, S0, r, strike, T):
+    """d price / d S0_i = E[e^{-rT} 1{basket > K} (1/D) S_T,i / S0_i]: the limit (epsilon -> 0, common random
+    numbers) of the bump-and-revalue loop basket_pricer.py:68-81; upstream re-simulates with FRESH noise per bump,
+    whose estimate is dominated by Monte-Carlo noise / epsilon (quirk documented in DESIGN.md)."""
+    S_T = asset_paths[:, -1, :]                       # (assets, sims)
+    D = S_T.shape[0]
+    ind = (S_T.mean(axis=0) > strike).astype(np.float64)
+    contrib = np.exp(-r * T) * ind[None, :] * S_T / (D * np.asarray(S0, dtype=np.float64)[:, None])
+    return contrib.mean(axis=1), contrib.std(axis=1) / np.sqrt(contrib.shape[1])
+
+
+def hjb_u_exact(t, X, T, D, MC=10 ** 5):
+    """hjb_implement.py:1085-1094 verbatim: t (NC, 1), X (NC, D) -> (NC, 1), NumPy global RNG."""
+    def g(Xv):
+        return np.log(0.5 + 0.5 * np.sum(Xv ** 2, axis=2, keepdims=True))
+    NC = t.shape[0]
+    W = np.random.normal(size=(MC, NC, D))
+    return -np.log(np.mean(np.exp(-g(X + np.sqrt(2.0 * np.abs(T - t)) * W)), axis=0))

@@ -18,7 +18,7 @@ def solver_cases():
     names = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         n = os.path.basename(f)[:-4]
-        if n not in ("mc_pricer", "bsb100_train_api"):
+        if n not in ("mc_pricer", "bsb100_train_api", "basket_pricer"):
             names.append(n)
     return names
 

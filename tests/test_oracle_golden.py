@@ -83,6 +83,45 @@ def test_mc_oracle_reproduces_reference(tag):
                - float(g[f"{tag}_analytic"])) < 1e-15
 
 
+def test_basket_pricer_oracle_reproduces_reference():
+    """oracle restatement of basket_pricer.py:41-66 vs the reference run under the same NumPy seed: bit-exact."""
+    g, _ = gu.load("basket_pricer")
+    cfg = json.loads(str(g["cfg"]))
+    np.random.seed(cfg["seed"])
+    paths = mco.simulate_asset_paths(g["S0"], cfg["r"], cfg["sigma"], cfg["T"], cfg["dt"], g["corr"], cfg["n"])
+    assert tuple(paths.shape) == tuple(g["paths_shape"])
+    assert np.array_equal(paths[:, -1, :8], g["paths_terminal_head"]) and paths.sum() == float(g["paths_sum"])
+    assert mco.mean_basket_price(paths, cfg["r"], cfg["strike"], cfg["T"]) == float(g["price"])
+    # pathwise deltas: consistent with a common-random-number central bump of the same oracle (noise-free check)
+    d, se = mco.pathwise_deltas(paths, g["S0"], cfg["r"], cfg["strike"], cfg["T"])
+    h = 1e-3
+    for i in (0, 4):
+        pr = []
+        for sgn in (+1, -1):
+            S = g["S0"].copy()
+            S[i] += sgn * h
+            np.random.seed(cfg["seed"])
+            pr.append(mco.mean_basket_price(mco.simulate_asset_paths(S, cfg["r"], cfg["sigma"], cfg["T"], cfg["dt"],
+                                                                     g["corr"], cfg["n"]), cfg["r"], cfg["strike"], cfg["T"]))
+        assert abs((pr[0] - pr[1]) / (2 * h) - d[i]) < 0.02 * abs(d[i]) + 1e-4
+
+
+def test_hjb_exact_oracle_terminal_and_jensen():
+    """hjb_u_exact restatement (hjb_implement.py:1085-1094; an inline closure upstream, so it cannot be imported):
+    u(T, x) = g(x) exactly, and -ln E[exp(-g)] <= E[g] (Jensen)."""
+    rng = np.random.RandomState(2)
+    X = rng.normal(size=(3, 5))
+    t = np.array([[0.0], [0.5], [1.0]])
+    np.random.seed(0)
+    u = mco.hjb_u_exact(t, X, 1.0, 5, MC=20000)
+    assert u.shape == (3, 1)
+    assert abs(u[2, 0] - np.log(0.5 + 0.5 * np.sum(X[2] ** 2))) < 1e-12
+    np.random.seed(0)
+    W = np.random.normal(size=(20000, 3, 5))
+    eg = np.mean(np.log(0.5 + 0.5 * np.sum((X + np.sqrt(2.0 * np.abs(1.0 - t)) * W) ** 2, axis=2)), axis=0)
+    assert np.all(u[:, 0] <= eg + 1e-12)
+
+
 def test_mc_moments_formula():
     np.random.seed(3)
     D = 6

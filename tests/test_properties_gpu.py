@@ -207,3 +207,76 @@ def test_mc_paths_and_pricer_share_streams_and_shard_exactly():
     # log-returns are Gaussian with the right per-step variance
     lr = np.log(paths[:, 1:] / paths[:, :-1]).reshape(-1, 12)
     assert abs(lr.std() - 0.2 * math.sqrt(1 / 9)) < 2e-3
+
+
+def test_mc_pathwise_deltas_match_oracle_and_bump_with_common_random_numbers():
+    """mc_basket_price_delta (basket_pricer.py:68-81): pathwise deltas vs the NumPy oracle's
+    pathwise estimator (statistical) and vs a central bump of the GPU price under common random numbers (exact
+    same Philox paths, so the comparison is noise-free up to O(eps^2) and fp32 rounding)."""
+    from oracle import mc_oracle as mco
+    import dnnpde_b200 as pde
+    Dm, n = 6, 1 << 20
+    np.random.seed(3)
+    model = pde.BlackScholesModel(0.05, 0.2, Dm, True)
+    S0 = np.linspace(0.9, 1.1, Dm)
+    pr = pde.MonteCarloPricer(model, pde.BasketOption(np.ones(Dm) / Dm, 1.0), 1.0, 10, n, seed=5)
+    price, deltas, se = pr.price_and_delta(S0, return_stderr=True)
+    assert abs(price - pr.price(S0)) <= 1e-12 * max(price, 1.0)            # same kernel body, same sums
+    np.random.seed(4)
+    paths = mco.simulate_asset_paths(S0, 0.05, 0.2, 1.0, 0.1, model.correlation, 200000)
+    od, ose = mco.pathwise_deltas(paths, S0, 0.05, 1.0, 1.0)
+    assert np.all(np.abs(deltas - od) <= 5 * ose + 1e-4), (deltas, od, ose)
+    assert abs(price - mco.mean_basket_price(paths, 0.05, 1.0, 1.0)) <= 5 * (se + 0.1 / math.sqrt(200000))
+    for i in (0, Dm - 1):                                                   # central bump, identical Philox streams
+        h = 2e-2
+        up, dn = S0.copy(), S0.copy()
+        up[i] += h
+        dn[i] -= h
+        fd = (pr.price(up) - pr.price(dn)) / (2 * h)
+        assert abs(fd - deltas[i]) <= 2e-3 * abs(deltas[i]) + 1e-5, (i, fd, deltas[i])
+    # sum_i S0_i delta_i = E[disc 1{B>K} B] >= price (homogeneity of the payoff in S0)
+    assert float(np.dot(S0, deltas)) >= price
+
+
+def test_basket_pricer_surface_matches_reference_layout():
+    """MonteCarloSimulator / BasketOptionPricer of basket_pricer.py:7-86 on the device generator."""
+    from oracle import mc_oracle as mco
+    import dnnpde_b200 as pde
+    bp = pde.basket_pricer
+    S0 = np.ones(4)
+    corr = np.full((4, 4), 0.3) + 0.7 * np.eye(4)
+    sim = bp.MonteCarloSimulator(S0, 0.05, 0.2, 1.0, 0.05, corr, seed=11)
+    paths = sim.simulate(100000)
+    assert paths.shape == (4, 21, 100000) and paths.dtype == np.float64 and np.allclose(paths[:, 0, :], 1.0)
+    pricer = bp.BasketOptionPricer(1.0, 1.0, corr, seed=11)
+    price = pricer.price(paths, 0.05)
+    np.random.seed(8)
+    ref_paths = mco.simulate_asset_paths(S0, 0.05, 0.2, 1.0, 0.05, corr, 100000)
+    ref = mco.mean_basket_price(ref_paths, 0.05, 1.0, 1.0)
+    assert abs(price - ref) <= 5 * 0.15 / math.sqrt(100000) * math.sqrt(2)
+    lr = np.log(paths[:, 1:, :] / paths[:, :-1, :])
+    c = np.corrcoef(lr.reshape(4, -1))
+    assert np.abs(c - corr).max() < 0.01                                    # increments carry the requested correlation
+    p2, deltas = pricer.price_and_delta(S0, paths, 0.05, 0.2, 1.0, 0.05)
+    od, ose = mco.pathwise_deltas(ref_paths, S0, 0.05, 1.0, 1.0)
+    assert p2 == price and np.all(np.abs(deltas - od) <= 5 * ose + 2e-4)
+
+
+def test_hjb_cole_hopf_exact_matches_oracle_and_terminal_condition():
+    """mc_hjb_exact (hjb_implement.py:1085-1094) vs the NumPy restatement; at t = T the
+    formula collapses to g(X) exactly."""
+    from oracle import mc_oracle as mco
+    import dnnpde_b200 as pde
+    D, NC, T = 20, 7, 1.0
+    rng = np.random.RandomState(0)
+    t = np.linspace(0, T, NC)[:, None]
+    X = rng.normal(size=(NC, D)) * 0.7
+    got = pde.hjb_u_exact(t, X, T, MC=400000, seed=9)
+    np.random.seed(1)
+    ref = mco.hjb_u_exact(t, X, T, D, MC=100000)
+    assert got.shape == (NC, 1) and got.dtype == np.float64
+    assert np.abs(got - ref).max() <= 5e-3, (got.ravel(), ref.ravel())       # MC noise of the 1e5-sample oracle ~1e-3
+    g_T = np.log(0.5 + 0.5 * np.sum(X[-1] ** 2))
+    assert abs(got[-1, 0] - g_T) <= 1e-5 * max(1.0, abs(g_T))
+    again = pde.hjb_u_exact(t, X, T, MC=400000, seed=9)
+    assert np.array_equal(got, again)                                         # Philox: reproducible

@@ -339,19 +339,54 @@ struct ColJobs {
   int max_width;
 };
 
-__global__ void colsum_stage1_kernel(const ColJobs js) {
+// stage 1: 256 threads = 4 row groups x 64 column quads; every thread streams float4 rows with four loads in flight,
+// the four row groups are combined through shared memory in a fixed order (widths and ld are multiples of 4)
+__global__ void __launch_bounds__(256) colsum_stage1_kernel(const ColJobs js) {
   const ColJob& j = js.job[blockIdx.y];
   if (!j.A) return;
+  __shared__ float4 red[4][64];
   const long long r0 = (long long)blockIdx.x * js.rows_per_block;
   const long long r1 = min(js.rows, r0 + js.rows_per_block);
-  for (int c = threadIdx.x; c < j.width; c += blockDim.x) {
-    float acc = 0.f;
-    if (j.B) {
-      for (long long r = r0; r < r1; ++r) acc += j.A[r * j.ld + c] + j.y[r] * j.B[r * j.ld + c];
-    } else {
-      for (long long r = r0; r < r1; ++r) acc += j.A[r * j.ld + c];
+  const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  for (int c0 = 0; c0 < j.width; c0 += 256) {
+    const int c = c0 + 4 * cg;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < j.width) {
+      long long r = r0 + rg;
+      for (; r + 12 < r1; r += 16) {
+        float4 a[4], b[4];
+        float y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = ld4(j.A + (r + 4 * u) * j.ld + c);
+          if (j.B) b[u] = ld4(j.B + (r + 4 * u) * j.ld + c), y[u] = j.y[r + 4 * u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j.B) a[u].x = fmaf(y[u], b[u].x, a[u].x), a[u].y = fmaf(y[u], b[u].y, a[u].y),
+                   a[u].z = fmaf(y[u], b[u].z, a[u].z), a[u].w = fmaf(y[u], b[u].w, a[u].w);
+          acc.x += a[u].x, acc.y += a[u].y, acc.z += a[u].z, acc.w += a[u].w;
+        }
+      }
+      for (; r < r1; r += 4) {
+        float4 a = ld4(j.A + r * j.ld + c);
+        if (j.B) {
+          const float4 b = ld4(j.B + r * j.ld + c);
+          const float y = j.y[r];
+          a.x = fmaf(y, b.x, a.x), a.y = fmaf(y, b.y, a.y), a.z = fmaf(y, b.z, a.z), a.w = fmaf(y, b.w, a.w);
+        }
+        acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+      }
     }
-    j.part[(size_t)blockIdx.x * js.max_width + c] = acc;
+    red[rg][cg] = acc;
+    __syncthreads();
+    if (rg == 0 && c < j.width) {
+      float4 t = red[0][cg];
+#pragma unroll
+      for (int g = 1; g < 4; ++g) t.x += red[g][cg].x, t.y += red[g][cg].y, t.z += red[g][cg].z, t.w += red[g][cg].w;
+      st4(j.part + (size_t)blockIdx.x * js.max_width + c, t);
+    }
+    __syncthreads();
   }
 }
 __global__ void colsum_stage2_kernel(const ColJobs js) {

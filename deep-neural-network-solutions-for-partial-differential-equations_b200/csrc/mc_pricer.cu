@@ -9,8 +9,10 @@
 //                 up to rounding).  Register-tiled over 4 paths per thread, L^T and zsT in shared
 //                 memory; then the weighted terminal price w_d S0_d exp(drift + vol y) -> eT[d][p]
 //   3. payoff:    one thread per path sums its D contributions in a fixed order, discounted payoff, fp64 sums
-// All N*D normals per path are drawn, as the reference does (the bound is Philox + Box-Muller issue, ~18 issue
-// slots per normal); nothing is stored per path.
+// All N*D normals per path are drawn, as the reference does; nothing is stored per path.  The bound is instruction
+// issue: ~20 instructions per normal (Philox4x32-10: 5 IMAD.WIDE + 5 LOP3; Box-Muller: 2 MUFU + ~4 FP32), measured
+// 57 % of the issue slots with the XU / FMA / ALU pipes at 40-47 % each (profiles/r01_ncu_details_mc_basket_v2.txt).
+// Unroll depth (1-4) and 2-4 CTAs per SM were measured within 3 % of each other; <2 Philox blocks in flight, 4 CTAs> kept.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,11 +37,12 @@ struct McK {
 };
 
 // sum over the N steps of the standard normals of asset d on global path gp
+template <int UNROLL>
 __device__ __forceinline__ float step_normal_sum(uint64_t gp, int d, int N, const PhiloxKeys& keys) {
   float acc0 = 0.f, acc1 = 0.f;
   const int nfull = N >> 2;
   Philox4 ctr{(uint32_t)gp, (uint32_t)(gp >> 32), (uint32_t)d, 0u};
-#pragma unroll 2
+#pragma unroll UNROLL
   for (int q = 0; q < nfull; ++q) {
     float z[4];
     ctr.w = (uint32_t)q;
@@ -61,8 +64,8 @@ __device__ __forceinline__ float step_normal_sum(uint64_t gp, int d, int N, cons
 
 // GREEKS: also accumulates the pathwise deltas  d price / d S0_d = E[ disc 1{basket > K} w_d S_T,d ] / S0_d  (the
 // estimator basket_pricer.py:68-81 approximates by bump-and-revalue), one fp64 accumulator per asset in thread d.
-template <bool GREEKS>
-__global__ void __launch_bounds__(kMcThreads, 4)
+template <bool GREEKS, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kMcThreads, MINB)
 mc_basket_kernel(const McK k, const float* __restrict__ S0, const float* __restrict__ wts,
                  const float* __restrict__ cholT, int chol_in_smem, unsigned long long n_paths,
                  unsigned long long path_offset, uint64_t seed, double* __restrict__ part,
@@ -89,7 +92,7 @@ mc_basket_kernel(const McK k, const float* __restrict__ S0, const float* __restr
     for (int i = tid; i < D * kMcPB; i += kMcThreads) {
       const int p = i & (kMcPB - 1), d = i >> 6;
       const unsigned long long lp = base + p;
-      zsT[i] = lp < n_paths ? step_normal_sum(path_offset + lp, d, k.N, keys) : 0.f;
+      zsT[i] = lp < n_paths ? step_normal_sum<UNROLL>(path_offset + lp, d, k.N, keys) : 0.f;
     }
     __syncthreads();
     // ---- 2. y = L z (lower triangular), weighted terminal prices; 4 paths per thread
@@ -294,7 +297,7 @@ static int mc_make(const McSpec* spec, McK& k) {
   return 0;
 }
 
-template <bool GREEKS>
+template <bool GREEKS, int UNROLL, int MINB>
 static int mc_price_impl(const McSpec* spec, const float* S0, const float* weights, const float* chol_T,
                          uint64_t n_paths, uint64_t seed, uint64_t path_offset, void* scratch, double* sums_out,
                          double* delta_out, void* stream) {
@@ -302,12 +305,12 @@ static int mc_price_impl(const McSpec* spec, const float* S0, const float* weigh
   if (mc_make(spec, k) || !S0 || !weights || !scratch || !sums_out || n_paths == 0 || (GREEKS && !delta_out))
     return FBSNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  auto kern = mc_basket_kernel<GREEKS>;
+  auto kern = mc_basket_kernel<GREEKS, UNROLL, MINB>;
   size_t smem = (size_t)2 * k.D * kMcPB * sizeof(float);
   int chol_in_smem = 0;
   // four CTAs per SM (64 registers, <= 56 KB each) hide the Philox/MUFU latencies; L^T joins the batch buffers in
   // shared memory only when that still fits, otherwise the 5 %-of-the-time matvec reads it through L1
-  if (chol_T && smem + (size_t)k.D * k.D * sizeof(float) <= 56 * 1024) {
+  if (chol_T && smem + (size_t)k.D * k.D * sizeof(float) <= (size_t)(224 / MINB) * 1024) {
     chol_in_smem = 1;
     smem += (size_t)k.D * k.D * sizeof(float);
   }
@@ -352,13 +355,13 @@ size_t mc_scratch_bytes(void) { return (size_t)kMcMaxBlocks * (2 + 32 * kMcMaxDJ
 int mc_basket_price(const McSpec* spec, const float* S0, const float* weights, const float* chol_T,
                     uint64_t n_paths, uint64_t seed, uint64_t path_offset, void* scratch, double* sums_out,
                     void* stream) {
-  return mc_price_impl<false>(spec, S0, weights, chol_T, n_paths, seed, path_offset, scratch, sums_out, nullptr, stream);
+  return mc_price_impl<false, 2, 4>(spec, S0, weights, chol_T, n_paths, seed, path_offset, scratch, sums_out, nullptr, stream);
 }
 
 int mc_basket_price_delta(const McSpec* spec, const float* S0, const float* weights, const float* chol_T,
                           uint64_t n_paths, uint64_t seed, uint64_t path_offset, void* scratch, double* sums_out,
                           double* delta_sums_out, void* stream) {
-  return mc_price_impl<true>(spec, S0, weights, chol_T, n_paths, seed, path_offset, scratch, sums_out, delta_sums_out,
+  return mc_price_impl<true, 2, 4>(spec, S0, weights, chol_T, n_paths, seed, path_offset, scratch, sums_out, delta_sums_out,
                              stream);
 }
 

@@ -394,6 +394,17 @@ def run_ours(args):
             torch.cuda.empty_cache()
     del batches
     torch.cuda.empty_cache()
+    if not args.skip_small and args.paths != 100:
+        # the other end of BASELINE.json's range (configs[1]: M=100): launch-latency bound, replayed as one CUDA graph
+        a3 = argparse.Namespace(**vars(args))
+        a3.paths, a3.steps, a3.warmup = 100, 200, 20
+        sol3, b3, _ = make_solver(c, a3)
+        ms3, l3, _, _ = measure_value(c, a3, sol3, b3)
+        line["small_m"] = {"metric": METRIC, "value": 1e3 / ms3, "unit": "iters/s", "ms_per_step": ms3, "paths": 100,
+                           "steps": a3.steps, "warmup": a3.warmup, "precision": a3.precision, "gpu_launches": int(l3),
+                           "note": "M=100 (5 100 rows, L2-resident): bound by the latency of ~38 dependent launches"}
+        del sol3, b3
+        torch.cuda.empty_cache()
     if not args.skip_mc:
         line["mc"] = measure_mc(c, args)
     # CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample
@@ -427,6 +438,7 @@ def main():
     ap.add_argument("--cpu-sample-paths", type=int, default=256)
     ap.add_argument("--skip-mc", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-small", action="store_true", help="do not also time the M=100 configuration")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU gradient all-reduce: fused NVLink peer-memory kernel (default) or NCCL")
     ap.add_argument("--skip-fp32", action="store_true", help="do not also time the fp32 SIMT variant")

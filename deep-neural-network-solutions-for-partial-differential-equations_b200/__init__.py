@@ -12,12 +12,12 @@ from .mc_pricer import (AnalyticalBlackScholes, BasketOption, BlackScholesModel,
                         MonteCarloPricer)
 from .networks import Naisnet, Sine
 from .problems import (BasketCallOption, BlackScholesBarenblatt, BSPDETestCase, CallOption1D, CallOptionND,
-                       HamiltonJacobiBellman, hjb_u_exact, u_exact)
+                       HamiltonJacobiBellman, HestonFBSNN, hjb_u_exact, u_exact)
 
 build = _lib.build
 
 __all__ = ["FBSNN", "Sine", "Naisnet", "BlackScholesBarenblatt", "BasketCallOption", "BSPDETestCase",
-           "CallOption1D", "CallOptionND", "HamiltonJacobiBellman", "u_exact", "hjb_u_exact", "basket_pricer", "CorrelationMatrix",
+           "CallOption1D", "CallOptionND", "HamiltonJacobiBellman", "HestonFBSNN", "u_exact", "hjb_u_exact", "basket_pricer", "CorrelationMatrix",
            "BlackScholesModel", "BasketOption", "MonteCarloPricer", "AnalyticalBlackScholes", "build",
            "TrainingPhases", "PredictionGenerator",
            "parallel", "spec"]

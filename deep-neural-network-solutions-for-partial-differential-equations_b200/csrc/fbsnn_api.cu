@@ -49,7 +49,7 @@ static int num_sms() {
 constexpr int kMaxL = FBSNN_MAX_HIDDEN;
 
 struct Plan {
-  int D, N, L, ldx, ldi, d_in;
+  int D, N, L, ldx, ldi, d_in, Dn;   // Dn = Brownian (noise) dimension, = D except for Heston
   bool tf32;
   int kin, ldw;   // K extent / leading dimension of the input-width weight operands (padded to ldx in TF32 mode)
   size_t W1p, Winp[kMaxL + 2];
@@ -60,7 +60,7 @@ struct Plan {
   long long rows;
   int loss_blocks, col_blocks, col_rows_per_block, wg_split, wg_chunk, gsq_blocks;
   // offsets in floats
-  size_t xin, sdw, Y, zf, V, ev, ybar, inc, zraw, part_loss, part_wg, part_col, part_gsq;
+  size_t xin, sdw, Y, zf, V, ev, ybar, inc, zraw, part_loss, part_wg, part_col, part_gsq, umask;
   size_t g[kMaxL + 2], a[kMaxL + 2], delta[kMaxL + 2], szz[kMaxL + 2], hd[kMaxL + 2], h[kMaxL + 2],
       ht[kMaxL + 2], hb[kMaxL + 2];
   size_t Bm[kMaxL + 2], Rm[kMaxL + 2], Bbar[kMaxL + 2], Sm[kMaxL + 2], nstate[kMaxL + 2];
@@ -83,9 +83,16 @@ static int validate(const FbsnnSpec* s) {
     return fail(FBSNN_E_UNSUPPORTED, "unknown net_kind %d", s->net_kind);
   }
   if (s->act_kind < 0 || s->act_kind > 2) return fail(FBSNN_E_UNSUPPORTED, "unknown act_kind %d", s->act_kind);
-  if (s->mu_kind < 0 || s->mu_kind > 1 || s->sigma_kind < 0 || s->sigma_kind > 1 || s->phi_kind < 0 ||
-      s->phi_kind > 2 || s->g_kind < 0 || s->g_kind > 3)
+  if (s->mu_kind < 0 || s->mu_kind > 2 || s->sigma_kind < 0 || s->sigma_kind > 2 || s->phi_kind < 0 ||
+      s->phi_kind > 2 || s->g_kind < 0 || s->g_kind > 5)
     return fail(FBSNN_E_UNSUPPORTED, "problem callables outside the closed enumeration");
+  const bool heston = s->sigma_kind == FBSNN_SIGMA_HESTON || s->mu_kind == FBSNN_MU_HESTON;
+  if (heston && (s->sigma_kind != FBSNN_SIGMA_HESTON || s->mu_kind != FBSNN_MU_HESTON || s->D != 2 || s->noise_dim != 1))
+    return fail(FBSNN_E_UNSUPPORTED, "the Heston problem needs mu and sigma of kind HESTON, D = 2 states and noise_dim = 1");
+  if (!heston && s->noise_dim != 0 && s->noise_dim != s->D)
+    return fail(FBSNN_E_UNSUPPORTED, "noise_dim %d != D %d is only defined for the Heston problem", s->noise_dim, s->D);
+  if (s->zt_dims < 0 || s->zt_dims > s->D) return fail(FBSNN_E_BADARG, "zt_dims %d outside 0..D", s->zt_dims);
+
   if (s->precision != FBSNN_PREC_FP32 && s->precision != FBSNN_PREC_TF32 && s->precision != FBSNN_PREC_TF32X3)
     return fail(FBSNN_E_UNSUPPORTED, "unknown precision %d", s->precision);
   return 0;
@@ -100,7 +107,8 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   p.ldx = round_up(p.d_in, p.tf32 ? 32 : 4);
   p.kin = p.tf32 ? p.ldx : p.d_in;
   p.ldw = p.kin;
-  p.ldi = round_up(s->D, 4);
+  p.Dn = s->noise_dim > 0 ? s->noise_dim : s->D;
+  p.ldi = round_up(p.Dn, 4);
   p.nais = s->net_kind == FBSNN_NET_NAIS;
   p.rows = rows;
   p.H[0] = p.d_in;
@@ -130,6 +138,7 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   p.zf = take(R * p.ldx);
   p.part_loss = take(2 * (size_t)p.loss_blocks);
   p.ev = take(R);
+  if (s->clamp_u) p.umask = take(R);
   for (int l = 1; l <= p.L; ++l) {
     p.g[l] = take(R * p.H[l]);
     p.a[l] = take(R * p.H[l]);
@@ -185,6 +194,8 @@ static ProblemK problem_k(const FbsnnSpec* s, const Plan& p) {
   k.D = s->D, k.N = s->N, k.ldx = p.ldx;
   k.mu_kind = s->mu_kind, k.sigma_kind = s->sigma_kind, k.phi_kind = s->phi_kind, k.g_kind = s->g_kind;
   k.mu_c = s->mu_c, k.sigma_c = s->sigma_c, k.phi_c = s->phi_c, k.strike = s->strike;
+  k.zt_dims = s->zt_dims > 0 ? s->zt_dims : s->D;
+  k.h_kappa = s->h_kappa, k.h_theta = s->h_theta, k.h_xi = s->h_xi, k.h_rho = s->h_rho;
   return k;
 }
 
@@ -409,6 +420,11 @@ static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     int rc = dense<true, false>(s, g, EpiStore{ws + p.zf, p.ldx}, 1, st, "Du");
     if (rc) return rc;
   }
+  if (s->clamp_u) {
+    const long long thr = p.rows * 32;
+    clamp_u_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(ws + p.Y, ws + p.zf, p.ldx, p.rows, ws + p.umask);
+    LAUNCH_CHECK("clamp_u");
+  }
   return 0;
 }
 
@@ -418,6 +434,7 @@ static int run_loss(const FbsnnSpec* s, const Plan& p, float* ws, bool with_grad
   a.xin = ws + p.xin, a.zf = ws + p.zf, a.sdw = ws + p.sdw, a.Y = ws + p.Y, a.rows = p.rows;
   a.ev = ws + p.ev, a.part = ws + p.part_loss;
   a.ybar = with_grad ? ws + p.ybar : nullptr, a.V = with_grad ? ws + p.V : nullptr;
+  a.umask = s->clamp_u ? ws + p.umask : nullptr;
   loss_residual_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a);
   LAUNCH_CHECK("loss_residual");
   if (with_grad) {
@@ -560,16 +577,16 @@ static int gen_increments(const FbsnnSpec* s, const Plan& p, float* ws, long lon
                           uint64_t seed, uint64_t iteration, const long long* iter_dev, const float* chol,
                           cudaStream_t st) {
   const float sqrt_dt = (float)sqrt((double)T / (double)s->N);
-  const long long total = M * (long long)(s->N + 1) * ((s->D + 3) / 4);
+  const long long total = M * (long long)(s->N + 1) * ((p.Dn + 3) / 4);
   const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)num_sms() * 32);
   float* target = chol ? ws + p.zraw : ws + p.inc;
-  brownian_increments_kernel<<<blocks, 256, 0, st>>>(target, M, s->N, s->D, sqrt_dt, p.ldi, path_offset, seed,
+  brownian_increments_kernel<<<blocks, 256, 0, st>>>(target, M, s->N, p.Dn, sqrt_dt, p.ldi, path_offset, seed,
                                                      iteration, iter_dev);
   LAUNCH_CHECK("brownian_increments");
   if (chol) {  // inc[r, i] = sum_j zraw[r, j] * L[i][j]   (np.einsum('ij,mnj->mni'), with_corr...:339-341)
     GemmArgs g{};
-    g.M = (int)p.rows, g.N = p.ldi, g.Nb = s->D, g.kchunk = 0, g.nseg = 1;
-    g.seg[0] = GemmSeg{ws + p.zraw, chol, p.ldi, s->D, s->D};
+    g.M = (int)p.rows, g.N = p.ldi, g.Nb = p.Dn, g.kchunk = 0, g.nseg = 1;
+    g.seg[0] = GemmSeg{ws + p.zraw, chol, p.ldi, p.Dn, p.Dn};
     int rc = dense<true, true>(s, g, EpiStore{ws + p.inc, p.ldi}, 1, st, "chol", false);
     if (rc) return rc;
   }
@@ -605,8 +622,12 @@ static int loss_grad_impl(const FbsnnSpec* s, const float* params, float* grads,
     a.t = W ? t : nullptr, a.W = W, a.inc = W ? nullptr : ws + p.inc, a.ldi = p.ldi;
     a.Xi = Xi, a.xi_rows = xi_rows, a.M = M, a.T = T;
     a.xin = ws + p.xin, a.sdw = ws + p.sdw, a.X_out = X_out;
-    const long long thr = (long long)M * s->D;
-    path_advance_kernel<<<(unsigned)((thr + 127) / 128), 128, 0, st>>>(k, a);
+    if (s->sigma_kind == FBSNN_SIGMA_HESTON) {
+      path_advance_heston_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(k, a);
+    } else {
+      const long long thr = (long long)M * s->D;
+      path_advance_kernel<<<(unsigned)((thr + 127) / 128), 128, 0, st>>>(k, a);
+    }
     LAUNCH_CHECK("path_advance");
   }
   if ((rc = sweeps_forward(s, p, n, ws, with_grad, st))) return rc;
@@ -647,7 +668,7 @@ using namespace fbsnn;
 extern "C" {
 
 const char* fbsnn_last_error(void) { return g_err; }
-int fbsnn_version(void) { return 100; }
+int fbsnn_version(void) { return 101; }
 long long fbsnn_launch_count(void) { return g_launches; }
 void fbsnn_dense_timing(int enable) { g_timing = enable != 0; g_ntimed = 0; }
 // Sums the recorded dense-layer launches (caller has synchronised): out = {n_launches, total ms, total FLOPs,
@@ -728,8 +749,8 @@ int fbsnn_fetch_minibatch(const FbsnnSpec* spec, float T, int64_t n_paths, int64
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   if ((rc = gen_increments(spec, p, ws, n_paths, T, path_offset, seed, iteration, nullptr, chol, st))) return rc;
-  const long long thr = (long long)n_paths * spec->D;
-  cumsum_paths_kernel<<<(unsigned)((thr + 127) / 128), 128, 0, st>>>(ws + p.inc, p.ldi, W_out, t_out, n_paths, spec->N, spec->D, T);
+  const long long thr = (long long)n_paths * p.Dn;
+  cumsum_paths_kernel<<<(unsigned)((thr + 127) / 128), 128, 0, st>>>(ws + p.inc, p.ldi, W_out, t_out, n_paths, spec->N, p.Dn, T);
   LAUNCH_CHECK("cumsum_paths");
   return 0;
 }

@@ -11,6 +11,8 @@ struct ProblemK {
   int D, N, ldx;
   int mu_kind, sigma_kind, phi_kind, g_kind;
   float mu_c, sigma_c, phi_c, strike;
+  int zt_dims;                              // terminal Z penalty over the first zt_dims components (= D normally)
+  float h_kappa, h_theta, h_xi, h_rho;      // Heston only
 };
 
 // ----------------------------------------------------------------------------------------------------
@@ -123,6 +125,69 @@ __global__ void path_advance_kernel(const ProblemK p, const PathArgs a) {
   }
 }
 
+// Heston 2-factor path advance (heston_dnnpde.py:587-605, 636-641): state (S, v), ONE Brownian driver W (M, N+1, 1)
+// that the reference's einsum broadcasts over both diffusion columns, so
+//   S' = S + clamp(mu_c S) dt + (s00 + s01) dW,   v' = v + clamp(kappa (theta - v)) dt + (s10 + s11) dW
+// with s00 = sqrt(max(v,1e-8)) S, s11 = xi sqrt(max(v,1e-8)), s01 = rho s11, s10 = rho s00, every entry clamped
+// to +-100.  One thread per path; sdw[row] = [(s00+s01) dW, (s10+s11) dW] feeds the generic loss kernels.
+__device__ __forceinline__ float clamp100(float x) { return fminf(fmaxf(x, -100.f), 100.f); }
+__global__ void path_advance_heston_kernel(const ProblemK p, const PathArgs a) {
+  const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (m >= a.M) return;
+  const int N = p.N, ldx = p.ldx;
+  float S = a.Xi[(a.xi_rows == 1 ? 0 : m) * 2 + 0], v = a.Xi[(a.xi_rows == 1 ? 0 : m) * 2 + 1];
+  const long long row0 = m * (N + 1);
+  float tn = a.t ? a.t[row0] : 0.f;
+  float wn = a.W ? a.W[row0] : 0.f;
+  for (int n = 0; n <= N; ++n) {
+    const long long r = row0 + n;
+    float* xr = a.xin + r * ldx;
+    xr[0] = tn, xr[1] = S, xr[2] = v;
+    for (int c = 3; c < ldx; ++c) xr[c] = 0.f;
+    if (a.X_out) a.X_out[r * 2] = S, a.X_out[r * 2 + 1] = v;
+    if (n == N) break;
+    const float tn1 = a.t ? a.t[r + 1] : (float)((double)(n + 1) * (double)a.T / (double)N);
+    const float dt = __fsub_rn(tn1, tn);
+    float dw;
+    if (a.W) {
+      const float wn1 = a.W[r + 1];
+      dw = __fsub_rn(wn1, wn);
+      wn = wn1;
+    } else {
+      dw = a.inc[(r + 1) * a.ldi];
+    }
+    const float sq = sqrtf(fmaxf(v, 1e-8f));
+    const float sS = __fmul_rn(sq, S), sv = __fmul_rn(p.h_xi, sq);
+    const float s00 = clamp100(sS), s01 = clamp100(__fmul_rn(p.h_rho, sv));
+    const float s10 = clamp100(__fmul_rn(p.h_rho, sS)), s11 = clamp100(sv);
+    const float d0 = __fadd_rn(__fmul_rn(s00, dw), __fmul_rn(s01, dw));
+    const float d1 = __fadd_rn(__fmul_rn(s10, dw), __fmul_rn(s11, dw));
+    a.sdw[r * 2] = d0, a.sdw[r * 2 + 1] = d1;
+    const float muS = clamp100(__fmul_rn(p.mu_c, S));
+    const float muv = clamp100(__fmul_rn(p.h_kappa, __fsub_rn(p.h_theta, v)));
+    S = __fadd_rn(__fadd_rn(S, __fmul_rn(muS, dt)), d0);
+    v = __fadd_rn(__fadd_rn(v, __fmul_rn(muv, dt)), d1);
+    tn = tn1;
+  }
+}
+
+// u = max(u, 0) and Du <- Du * 1{u >= 0} (torch.clamp(u, min=0) and its autograd mask, heston_dnnpde.py:568-576).
+// mask (nullable) keeps 1{u_raw >= 0} for the seed kernel.
+__global__ void clamp_u_kernel(float* __restrict__ Y, float* __restrict__ zf, int ldx, long long rows,
+                               float* __restrict__ mask) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const bool keep = Y[r] >= 0.f;
+  if (!keep)
+    for (int c = lane; c < ldx; c += 32) zf[r * ldx + c] = 0.f;
+  __syncwarp();
+  if (lane == 0) {
+    if (!keep) Y[r] = 0.f;
+    if (mask) mask[r] = keep ? 1.f : 0.f;
+  }
+}
+
 // rows of arbitrary (t, X) for net_u: xin = [t, X, 0-pad]
 __global__ void pack_rows_kernel(const float* t, const float* X, long long rows, int D, int ldx, float* xin) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -185,6 +250,7 @@ struct LossArgs {
   float* ybar;
   float* V;
   float* part;   // [2][gridDim.x] partial sums: loss, sum(ybar)
+  const float* umask;   // nullable: 1{u_raw >= 0} per row (clamp_u): scales the seeds
 };
 
 __device__ __forceinline__ void terminal_g(const ProblemK& p, float sumx, float sumx2, float& g, float& dg_scale) {
@@ -202,6 +268,21 @@ __device__ __forceinline__ void terminal_g(const ProblemK& p, float sumx, float 
     g = fmaxf(base - p.strike, 0.f);
     dg_scale = base > p.strike ? sc : (base == p.strike ? 0.5f * sc : 0.f);  // torch.maximum splits ties
   }
+}
+// payoffs of the first state component only (Heston: X = (S, v)): g(S) and dg/dS
+__device__ __forceinline__ void terminal_g_first(const ProblemK& p, float x0, float& g, float& dg) {
+  const float s = x0 - p.strike;
+  if (p.g_kind == FBSNN_G_CALL_FIRST) {
+    g = fmaxf(s, 0.f);
+    dg = s > 0.f ? 1.f : (s == 0.f ? 0.5f : 0.f);
+  } else {                                   // (S-K) / (1 + exp(-alpha (S-K))), alpha = 10
+    const float q = 1.f / (1.f + expf(-10.f * s));   // sigmoid(10 s)
+    g = s * q;
+    dg = q + 10.f * s * q * (1.f - q);               // = q + 10 s e / (1+e)^2 without the inf/inf at s << 0
+  }
+}
+__device__ __forceinline__ bool g_is_first(const ProblemK& p) {
+  return p.g_kind == FBSNN_G_CALL_FIRST || p.g_kind == FBSNN_G_CALL_FIRST_SMOOTH;
 }
 
 __global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
@@ -236,11 +317,14 @@ __global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
       for (int d = lane; d < p.D; d += 32) { const float xv = x[d]; sx += xv; sx2 = fmaf(xv, xv, sx2); }
       sx = warp_sum(sx), sx2 = warp_sum(sx2);
       float g, dgs;
-      terminal_g(p, sx, sx2, g, dgs);
+      const bool first = g_is_first(p);
+      if (first) terminal_g_first(p, x[0], g, dgs);
+      else terminal_g(p, sx, sx2, g, dgs);
       const bool mulx = p.g_kind == FBSNN_G_SUMSQ || p.g_kind == FBSNN_G_LOGQ;
       float zt = 0.f;
-      for (int d = lane; d < p.D; d += 32) {
-        const float diff = z[d] - (mulx ? dgs * x[d] : dgs);
+      for (int d = lane; d < p.zt_dims; d += 32) {
+        const float dg = first ? (d == 0 ? dgs : 0.f) : (mulx ? dgs * x[d] : dgs);
+        const float diff = z[d] - dg;
         zt = fmaf(diff, diff, zt);
       }
       zt = warp_sum(zt);
@@ -283,10 +367,21 @@ __global__ void loss_seed_kernel(const ProblemK p, const LossArgs a) {
       for (int d = lane; d < p.D; d += 32) { const float xv = x[d]; sx += xv; sx2 = fmaf(xv, xv, sx2); }
       sx = warp_sum(sx), sx2 = warp_sum(sx2);
       float g, dgs;
-      terminal_g(p, sx, sx2, g, dgs);
+      const bool first = g_is_first(p);
+      if (first) terminal_g_first(p, x[0], g, dgs);
+      else terminal_g(p, sx, sx2, g, dgs);
       const bool mulx = p.g_kind == FBSNN_G_SUMSQ || p.g_kind == FBSNN_G_LOGQ;
       yb = 2.f * e + (p.N > 0 ? 2.f * a.ev[r - 1] : 0.f);
-      for (int d = lane; d < p.D; d += 32) v[1 + d] = 2.f * (z[d] - (mulx ? dgs * x[d] : dgs));
+      for (int d = lane; d < p.D; d += 32) {
+        const float dg = first ? (d == 0 ? dgs : 0.f) : (mulx ? dgs * x[d] : dgs);
+        v[1 + d] = d < p.zt_dims ? 2.f * (z[d] - dg) : 0.f;
+      }
+    }
+    if (a.umask) {                            // clamp_u: d max(u,0)/du and d(mask Du)/dDu
+      const float mk = a.umask[r];
+      yb *= mk;
+      __syncwarp();
+      for (int d = lane; d < p.D; d += 32) v[1 + d] *= mk;
     }
     if (lane == 0) {
       v[0] = 0.f;
@@ -468,6 +563,7 @@ struct OptState {
   long long step;                                    // Adam step (reset when a new optimiser is created)
   float clip_coef, step_size, bc2_sqrt, grad_norm;
   long long rng_iter;                                // Philox iteration counter of fbsnn_train_step (never reset)
+  int skip;                                          // 1: this iteration's gradient was not finite, no update
 };
 
 __global__ void gradsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
@@ -582,20 +678,23 @@ __global__ void opt_prepare_kernel(const float* __restrict__ part, int npart, Fb
     const float norm = (float)sqrt(acc);
     float coef = 1.f;
     if (hp.max_grad_norm > 0.0) coef = fminf((float)hp.max_grad_norm / (norm + 1e-6f), 1.f);
+    st->rng_iter += 1;
+    st->grad_norm = norm;
+    st->skip = (hp.skip_nonfinite != 0.0 && !isfinite(norm)) ? 1 : 0;
+    if (st->skip) return;
     const long long step = st->step + 1;
     const double bc1 = 1.0 - pow(hp.beta1, (double)step);
     const double bc2 = 1.0 - pow(hp.beta2, (double)step);
     st->step = step;
-    st->rng_iter += 1;
     st->clip_coef = coef;
     st->step_size = (float)(hp.lr / bc1);
     st->bc2_sqrt = (float)sqrt(bc2);
-    st->grad_norm = norm;
   }
 }
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float beta1, float beta2, float eps,
                             const OptState* __restrict__ st) {
+  if (st->skip) return;
   const float coef = st->clip_coef, step_size = st->step_size, bc2s = st->bc2_sqrt;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * coef;

@@ -66,6 +66,8 @@ class FBSNN(ABC):
     _train_returns = "quad"          # "graph" | "triple" | "quad"
     _clip_norm: Optional[float] = 1.0  # with_corr...:424; DeepBSDE has no clipping
     _schedule_kind = "mm"            # "mm" (1d/nd/hjb) | "recursive" (with_corr) -- only with n_schedule="reference"
+    _skip_nonfinite = False          # heston_dnnpde.py:408-410: NaN-loss iterations are skipped
+    _check_layers = True             # layers[0] == D + 1 (the Heston class swaps its input layer afterwards)
 
     def __init__(self, Xi, T, M, N, D, *args, **kw):
         # two reference arities: (layers, mode, activation) and (Mm, layers, mode, activation[, correlation_type])
@@ -103,7 +105,7 @@ class FBSNN(ABC):
         self.mode = mode
         self.activation = activation
         self.activation_function = make_activation(activation)
-        if list(layers)[0] != D + 1 or list(layers)[-1] != 1:
+        if self._check_layers and (list(layers)[0] != D + 1 or list(layers)[-1] != 1):
             raise ValueError(f"layers must start with D+1={D + 1} and end with 1, got {list(layers)}")
         self.layers = list(layers)
         self.model = build_model(self.layers, mode, self.activation_function).to(self.device)
@@ -137,6 +139,22 @@ class FBSNN(ABC):
         self.use_cuda_graph = bool(extras.get("cuda_graph", True))
         self._peer = None
         self.collective = extras.get("collective", "peer")   # multi-GPU: "peer" (fused NVLink kernel) | "nccl"
+
+    @property
+    def _sdim(self) -> int:
+        """State dimension the kernels see (= D; the Heston class carries (S, v) on one Brownian driver)."""
+        return self.D
+
+    def _state_xi(self, Xi: torch.Tensor) -> torch.Tensor:
+        """(rows, state dim) initial condition from the caller's Xi."""
+        return Xi.reshape(-1, self.D)
+
+    def _fill_problem(self, sp: S.FbsnnSpec) -> None:
+        ps = self.problem_spec
+        sp.mu_kind, sp.mu_c = ps.mu_kind, ps.mu_c
+        sp.sigma_kind, sp.sigma_c = ps.sigma_kind, ps.sigma_c
+        sp.phi_kind, sp.phi_c = ps.phi_kind, ps.phi_c
+        sp.g_kind, sp.strike = ps.g_kind, self.strike
 
     # ------------------------------------------------------------------------------------------------
     # host-side pieces kept verbatim in meaning
@@ -232,14 +250,10 @@ class FBSNN(ABC):
 
     def _spec(self, N: Optional[int] = None) -> S.FbsnnSpec:
         sp = S.FbsnnSpec()
-        ps = self.problem_spec
-        sp.D, sp.N = self.D, self.N if N is None else N
+        sp.D, sp.N = self._sdim, self.N if N is None else N
         sp.net_kind = S.NET_FC if self.mode == "FC" else S.NET_NAIS
         sp.act_kind = S.ACT[self.activation]
-        sp.mu_kind, sp.mu_c = ps.mu_kind, ps.mu_c
-        sp.sigma_kind, sp.sigma_c = ps.sigma_kind, ps.sigma_c
-        sp.phi_kind, sp.phi_c = ps.phi_kind, ps.phi_c
-        sp.g_kind, sp.strike = ps.g_kind, self.strike
+        self._fill_problem(sp)
         sp.nais_eps = 0.01
         sp.precision = S.PRECISION[self.precision]
         self._fp.fill_spec(sp)
@@ -294,7 +308,7 @@ class FBSNN(ABC):
         with torch.cuda.device(self.device):
             ws = self._workspace(lib, sp, max(1, math.ceil(rows / (sp.N + 1))), False)
             u = torch.empty(rows, 1, device=self.device)
-            du = torch.empty(rows, self.D, device=self.device)
+            du = torch.empty(rows, self._sdim, device=self.device)
             _lib.check(lib.fbsnn_net_u(ctypes.byref(sp), _ptr(self._fp.flat), _ptr(t), _ptr(X), rows, _ptr(ws),
                                        ws.numel(), _ptr(u), _ptr(du), self._stream()), "fbsnn_net_u")
         return u, du
@@ -316,16 +330,16 @@ class FBSNN(ABC):
             raise ValueError(f"W has {N} steps but self.N = {self.N}")
         if W.shape[2] != self.D or t.shape[:2] != W.shape[:2]:
             raise ValueError(f"bad shapes t{tuple(t.shape)} W{tuple(W.shape)} for D={self.D}")
-        Xi = self._as_f32(Xi, self.device).reshape(-1, self.D)
+        Xi = self._state_xi(self._as_f32(Xi, self.device)).contiguous()
         if Xi.shape[0] not in (1, M):
             raise ValueError(f"Xi has {Xi.shape[0]} rows, expected 1 or {M}")
         sp = self._spec()
         dev = self.device
         with torch.cuda.device(dev):
             ws = self._workspace(lib, sp, M, with_grad)
-            X = torch.empty(M, N + 1, self.D, device=dev)
+            X = torch.empty(M, N + 1, self._sdim, device=dev)
             Y = torch.empty(M, N + 1, 1, device=dev)
-            Z = torch.empty(M, N + 1, self.D, device=dev) if want_Z else None
+            Z = torch.empty(M, N + 1, self._sdim, device=dev) if want_Z else None
             loss = torch.empty((), device=dev)
             if with_grad:
                 rc = lib.fbsnn_loss_grad(ctypes.byref(sp), _ptr(self._fp.flat), _ptr(self._fp.grad), _ptr(t), _ptr(W),
@@ -358,7 +372,8 @@ class FBSNN(ABC):
     def predict(self, Xi_star, t_star, W_star):
         """(X_star, Y_star) (DeepBSDE.py:297-302; with_corr...:455-486).  Accepts NumPy or tensors, broadcasts
         singleton batch dimensions and, like the reference, sets self.M to the batch size."""
-        Xi_star = self._as_f32(Xi_star, self.device).reshape(-1, self.D)
+        Xi_star = self._as_f32(Xi_star, self.device)
+        Xi_star = Xi_star.reshape(-1, Xi_star.shape[-1] if Xi_star.dim() > 1 else self.D)
         t_star = self._as_f32(t_star, self.device)
         W_star = self._as_f32(W_star, self.device)
         batch = max(Xi_star.shape[0], t_star.shape[0], W_star.shape[0])
@@ -408,7 +423,7 @@ class FBSNN(ABC):
         dev = self.device
         previous_it = self.iteration[-1] if self.iteration else 0
         self.begin_training(learning_rate)
-        track_min = self._train_returns != "graph"
+        track_min = self._train_returns not in ("graph", "heston")
         loss_buf = torch.zeros(N_Iter + 1, device=dev)
         y0_buf = torch.zeros(N_Iter + 1, device=dev)
         time_logs = []
@@ -442,10 +457,14 @@ class FBSNN(ABC):
                     start = time.time()
                     self.training_loss.append(vals.mean())
                     self.iteration.append(it)
+                    if self._train_returns == "heston":
+                        self.Y0_values.append(float(y0_buf[k]))
             self.last_losses = loss_buf[:N_Iter].cpu().numpy()     # device -> host read of the step results
             self.last_Y0 = y0_buf[:N_Iter].cpu().numpy()
         # p.grad = the gradient the last Adam step used (summed over ranks on the multi-GPU peer path)
         self._fp.attach_grads(self._peer["sum"][:self._fp.n] if self._peer is not None else None)
+        if self._train_returns == "heston":               # heston_dnnpde.py:448
+            return np.column_stack((self.iteration, self.training_loss, self.Y0_values))
         graph = np.stack((self.iteration, self.training_loss))
         if self._train_returns == "graph":
             return graph
@@ -461,7 +480,8 @@ class FBSNN(ABC):
             self._opt_state = torch.zeros(S.OPT_STATE_BYTES, dtype=torch.uint8, device=self.device)
         self._opt_state[:24].zero_()       # Adam step counter; the Philox iteration counter at byte 24 lives on
         self.optimizer = {"type": "Adam", "lr": learning_rate, "betas": (0.9, 0.999), "eps": 1e-8}
-        self._hp = S.FbsnnAdam(learning_rate, 0.9, 0.999, 1e-8, self._clip_norm if self._clip_norm else 0.0)
+        self._hp = S.FbsnnAdam(learning_rate, 0.9, 0.999, 1e-8, self._clip_norm if self._clip_norm else 0.0,
+                               1.0 if self._skip_nonfinite else 0.0)
         self._n_train_calls += 1
 
     def _step(self, t_b, W_b, loss_out, want_X, k, alias_inputs=False):
@@ -515,7 +535,7 @@ class FBSNN(ABC):
         lo, hi = self._shard()
         m_loc = hi - lo
         ws = self._workspace(lib, sp, m_loc, True)
-        X = torch.empty(m_loc, self.N + 1, self.D, device=dev) if want_X else None
+        X = torch.empty(m_loc, self.N + 1, self._sdim, device=dev) if want_X else None
         Y = torch.empty(m_loc, self.N + 1, 1, device=dev)
         if W_b is not None:
             if W_b.shape[0] == self.M and m_loc != self.M:
@@ -526,8 +546,8 @@ class FBSNN(ABC):
             chol = None
         else:
             chol = self._chol_device()
-        Xi = self.Xi.detach().reshape(-1, self.D)
-        xi_loc = Xi if Xi.shape[0] == 1 else Xi[lo:hi].contiguous()
+        Xi = self._state_xi(self.Xi.detach())
+        xi_loc = Xi.contiguous() if Xi.shape[0] == 1 else Xi[lo:hi].contiguous()
         seed = self.seed & 0xFFFFFFFFFFFFFFFF
         if not dp:
             rc = lib.fbsnn_train_step(ctypes.byref(sp), ctypes.byref(self._hp), _ptr(fp.flat), _ptr(fp.grad),

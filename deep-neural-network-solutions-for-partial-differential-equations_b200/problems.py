@@ -181,3 +181,119 @@ class HamiltonJacobiBellman(FBSNN):
 
     def sigma_tf(self, t, X, Y):
         return math.sqrt(2.0) * super().sigma_tf(t, X, Y)
+
+
+class HestonFBSNN(FBSNN):
+    """Heston 2-factor FBSNN (heston_dnnpde.py:519-699): state (S, v) on ONE Brownian driver (the reference passes
+    D = 1 to its base class and lets einsum broadcast dW over both diffusion columns), network input (t, S, v),
+    u clamped at 0, outputs (u, dU/dS, dU/dv), terminal call payoff on S ('discontinuous') or its sigmoid-smoothed
+    form ('continuous'), phi = r Y.  train() follows that file: N-schedule from Mm, clip 1.0, log every 100,
+    returns column_stack((iteration, training_loss, Y0_values))."""
+    _check_layers = False
+    _skip_nonfinite = True
+    _log_every = 100
+    _train_returns = "heston"
+    _clip_norm = 1.0
+    _schedule_kind = "mm"
+
+    def __init__(self, Xi, T, M, N, D, Mm, layers, mode, activation, correlation_type="no_correlation", kappa=2.0,
+                 theta=0.2, sigma=0.3, rho=0.8, v0=0.2, payoff_type='discontinuous', **kw):
+        import torch.nn as nn
+
+        from .networks import FlatParams
+        if payoff_type not in ("discontinuous", "continuous"):
+            raise ValueError("Invalid payoff type. Choose 'discontinuous' or 'continuous'.")
+        kw.setdefault("n_schedule", None)
+        super().__init__(Xi, T, M, N, 1, Mm, layers, mode, activation, correlation_type, **kw)
+        self.kappa, self.theta, self.sigma, self.rho, self.v0 = kappa, theta, sigma, rho, v0
+        self.payoff_type = payoff_type
+        self.y0_values = []
+        self.Y0_values = []
+        layers = list(layers)
+        # swap the input layer(s) for 3 inputs (t, S, v), exactly in the reference's order (RNG stream), :533-544
+        if self.mode == "FC":
+            self.model[0] = nn.Linear(in_features=3, out_features=layers[1]).to(self.device)
+        else:
+            self.model.layer1 = nn.Linear(in_features=3, out_features=layers[1]).to(self.device)
+            self.model.layer2_input = nn.Linear(in_features=3, out_features=layers[2]).to(self.device)
+            if len(layers) >= 5:
+                self.model.layer3_input = nn.Linear(in_features=3, out_features=layers[3]).to(self.device)
+            if len(layers) == 6:
+                self.model.layer4_input = nn.Linear(in_features=3, out_features=layers[4]).to(self.device)
+            self.model.layers = [3] + layers[1:]
+        self.layers = [3] + layers[1:]
+        self.initialize_weights()
+        self._fp = FlatParams(self.model, "FC" if self.mode == "FC" else "NAIS", self.device)
+        self.problem_spec = S.ProblemSpec(S.MU_HESTON, 0.05, S.SIGMA_HESTON, 0.0, S.PHI_RY, 0.05,
+                                          S.G_CALL_FIRST if payoff_type == "discontinuous" else S.G_CALL_FIRST_SMOOTH)
+
+    @property
+    def _sdim(self):
+        return 2
+
+    def _state_xi(self, Xi):
+        """[S0, v0] rows: the caller's Xi carries S0 only (:621-626); predict() may pass (S, v) pairs (:668-671)."""
+        Xi = Xi.reshape(-1, Xi.shape[-1] if Xi.dim() > 1 else 1)
+        if Xi.shape[1] == 1:
+            Xi = torch.cat([Xi, torch.full_like(Xi, self.v0)], dim=1)
+        return Xi[:, :2]
+
+    def _fill_problem(self, sp):
+        super()._fill_problem(sp)
+        sp.noise_dim, sp.clamp_u, sp.zt_dims = 1, 1, 1
+        sp.h_kappa, sp.h_theta, sp.h_xi, sp.h_rho, sp.h_v0 = self.kappa, self.theta, self.sigma, self.rho, self.v0
+
+    def initialize_weights(self):
+        for param in self.model.parameters():           # heston_dnnpde.py:580-585
+            if len(param.shape) > 1:
+                torch.nn.init.xavier_uniform_(param, gain=0.5)
+            else:
+                torch.nn.init.zeros_(param)
+
+    def net_u(self, t, X):
+        """(u, dU/dS, dU/dv) for X = (S, v) rows (:560-577)."""
+        X = self._as_f32(X, self.device)
+        if X.dim() == 1:
+            X = X.unsqueeze(0)
+        u, du = super().net_u(t, X)
+        return u, du[:, 0:1], du[:, 1:2]
+
+    def predict(self, Xi_star, t_star, W_star):
+        X, Y = super().predict(Xi_star, t_star, W_star)
+        return X[:, :, 0:1], X[:, :, 1:2], Y             # S, v, Y (:683)
+
+    def calculate_greeks(self, S, v, t):
+        """(Y, delta, gamma) on a grid (:685-699).  delta is the analytic in-kernel dU/dS; gamma -- a second
+        autograd pass upstream -- is a central difference of delta (net_u outputs are not autograd-differentiable)."""
+        import numpy as np
+        S = np.asarray(S, dtype=np.float32).reshape(-1)
+        v = np.asarray(v, dtype=np.float32).reshape(-1)
+        t = np.broadcast_to(np.asarray(t, dtype=np.float32).reshape(-1), S.shape).copy()
+        h = 1e-3 * np.maximum(np.abs(S), 1.0)
+        Y, delta, _ = self.net_u(t[:, None], np.stack([S, v], -1))
+        _, dp, _ = self.net_u(t[:, None], np.stack([S + h, v], -1))
+        _, dm, _ = self.net_u(t[:, None], np.stack([S - h, v], -1))
+        gamma = (dp - dm).cpu().numpy()[:, 0] / (2 * h)
+        return Y.cpu().numpy(), delta.cpu().numpy(), gamma[:, None]
+
+    def phi_tf(self, t, X, Y, Z):
+        return 0.05 * Y
+
+    def g_tf(self, X):
+        Sv = X[:, 0:1] if X.dim() > 1 else X
+        if self.payoff_type == 'discontinuous':
+            return torch.maximum(Sv - self.strike, torch.tensor(0.0).to(Sv.device))
+        return (Sv - self.strike) / (1 + torch.exp(-10.0 * (Sv - self.strike)))
+
+    def mu_tf(self, t, X, Y=None, Z=None):
+        Sv, v = X[:, 0:1], X[:, 1:2]
+        return torch.cat([0.05 * Sv, self.kappa * (self.theta - v)], dim=1).clamp(-100, 100)
+
+    def sigma_tf(self, t, X, Y=None):
+        Sv, v = X[:, 0:1], X[:, 1:2]
+        sS = torch.sqrt(torch.clamp(v, min=1e-8)) * Sv
+        sv = self.sigma * torch.sqrt(torch.clamp(v, min=1e-8))
+        m = torch.zeros((Sv.shape[0], 2, 2), device=X.device)
+        m[:, 0, 0], m[:, 1, 1] = sS.squeeze(-1), sv.squeeze(-1)
+        m[:, 0, 1], m[:, 1, 0] = self.rho * sv.squeeze(-1), self.rho * sS.squeeze(-1)
+        return m.clamp(-100, 100)

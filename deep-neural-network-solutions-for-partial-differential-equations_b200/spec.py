@@ -9,10 +9,10 @@ OPT_STATE_BYTES = 2048
 
 NET_FC, NET_NAIS = 0, 1
 ACT = {"Sine": 0, "ReLU": 1, "Tanh": 2}
-MU_ZERO, MU_LINEAR = 0, 1
-SIGMA_CONST, SIGMA_PROP = 0, 1
+MU_ZERO, MU_LINEAR, MU_HESTON = 0, 1, 2
+SIGMA_CONST, SIGMA_PROP, SIGMA_HESTON = 0, 1, 2
 PHI_BSB, PHI_RY, PHI_ZSQ = 0, 1, 2
-G_SUMSQ, G_CALL_SUM, G_CALL_MEAN, G_LOGQ = 0, 1, 2, 3
+G_SUMSQ, G_CALL_SUM, G_CALL_MEAN, G_LOGQ, G_CALL_FIRST, G_CALL_FIRST_SMOOTH = 0, 1, 2, 3, 4, 5
 PRECISION = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 
@@ -30,12 +30,14 @@ class FbsnnSpec(C.Structure):
         ("off_Win", C.c_int64 * (MAX_HIDDEN + 2)),
         ("off_bin", C.c_int64 * (MAX_HIDDEN + 2)),
         ("n_params", C.c_int64),
+        ("noise_dim", C.c_int32), ("clamp_u", C.c_int32), ("zt_dims", C.c_int32),
+        ("h_kappa", C.c_float), ("h_theta", C.c_float), ("h_xi", C.c_float), ("h_rho", C.c_float), ("h_v0", C.c_float),
     ]
 
 
 class FbsnnAdam(C.Structure):
     _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
-                ("max_grad_norm", C.c_double)]
+                ("max_grad_norm", C.c_double), ("skip_nonfinite", C.c_double)]
 
 
 class McSpec(C.Structure):

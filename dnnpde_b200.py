@@ -10,7 +10,7 @@ if _root not in sys.path:
 _REAL = "deep-neural-network-solutions-for-partial-differential-equations_b200"
 _pkg = importlib.import_module(_REAL)
 for _sub in ("DeepBSDE", "with_corr_high_dimension_pde", "hjb_implement", "nd_BSPDE_case", "bspde_1d_case",
-             "numerics", "numerics.multidimensional_mc_pricer"):
+             "numerics", "numerics.multidimensional_mc_pricer", "heston_dnnpde", "basket_pricer"):
     importlib.import_module(_REAL + "." + _sub)
 # one module object per submodule, reachable under both names (no duplicate class objects)
 for _name, _mod in list(sys.modules.items()):

@@ -29,10 +29,14 @@ enum { FBSNN_NET_FC = 0, FBSNN_NET_NAIS = 1 };
 /* activation: Functions/Sine.py:6-12, nn.ReLU, nn.Tanh (with_corr_high_dimension_pde.py:157-162) */
 enum { FBSNN_ACT_SINE = 0, FBSNN_ACT_RELU = 1, FBSNN_ACT_TANH = 2 };
 /* closed enumeration of the reference's mu_tf / sigma_tf / phi_tf / g_tf callables */
-enum { FBSNN_MU_ZERO = 0, FBSNN_MU_LINEAR = 1 };            /* 0 | mu_c * X                                   */
-enum { FBSNN_SIGMA_CONST = 0, FBSNN_SIGMA_PROP = 1 };       /* sigma_c * I | sigma_c * diag(X)                */
+enum { FBSNN_MU_ZERO = 0, FBSNN_MU_LINEAR = 1,              /* 0 | mu_c * X                                   */
+       FBSNN_MU_HESTON = 2 };                               /* [mu_c S, kappa (theta - v)], clamped to +-100  */
+enum { FBSNN_SIGMA_CONST = 0, FBSNN_SIGMA_PROP = 1,         /* sigma_c * I | sigma_c * diag(X)                */
+       FBSNN_SIGMA_HESTON = 2 };                            /* 2x2 Heston diffusion (heston_dnnpde.py:593-605) */
 enum { FBSNN_PHI_BSB = 0, FBSNN_PHI_RY = 1, FBSNN_PHI_ZSQ = 2 }; /* c(Y - X.Z) | c Y | |Z|^2                   */
-enum { FBSNN_G_SUMSQ = 0, FBSNN_G_CALL_SUM = 1, FBSNN_G_CALL_MEAN = 2, FBSNN_G_LOGQ = 3 };
+enum { FBSNN_G_SUMSQ = 0, FBSNN_G_CALL_SUM = 1, FBSNN_G_CALL_MEAN = 2, FBSNN_G_LOGQ = 3,
+       FBSNN_G_CALL_FIRST = 4,                              /* max(X_0 - K, 0)            (heston_dnnpde.py:548-550) */
+       FBSNN_G_CALL_FIRST_SMOOTH = 5 };                     /* (X_0-K)/(1+exp(-10 (X_0-K))) (heston_dnnpde.py:551-556) */
 /* arithmetic variant of the dense layers */
 enum { FBSNN_PREC_FP32 = 0,      /* SIMT fp32 FMA: parity-grade (tolerances in tests/test_parity_gpu.py)     */
        FBSNN_PREC_TF32 = 1,      /* tcgen05 kind::tf32, fp32 accumulate in TMEM: large-M throughput variant  */
@@ -55,12 +59,19 @@ typedef struct FbsnnSpec {
   int64_t off_Win[FBSNN_MAX_HIDDEN + 2];  /* NAIS layer{l}_input.weight (l = 2..L)                            */
   int64_t off_bin[FBSNN_MAX_HIDDEN + 2];
   int64_t n_params;                       /* length of the flat buffers in floats (incl. alignment padding)   */
+  /* ---- version 101: Heston 2-factor problem (heston_dnnpde.py:519-659); all zero for the other problems ---- */
+  int32_t noise_dim;                      /* columns of W; 0 = D.  Heston: D = 2 states (S, v), ONE Brownian driver */
+  int32_t clamp_u;                        /* 1: u = max(net, 0), Du masked accordingly (heston_dnnpde.py:568)  */
+  int32_t zt_dims;                        /* terminal |Z - grad g|^2 over the first zt_dims components; 0 = all D */
+  float h_kappa, h_theta, h_xi, h_rho, h_v0;   /* mean reversion, long-run variance, vol of vol, correlation, v(0) */
 } FbsnnSpec;
 
 /* Adam + clip_grad_norm_ hyper-parameters (torch.optim.Adam defaults, DeepBSDE.py:272;
  * clip: with_corr_high_dimension_pde.py:424).  max_grad_norm <= 0 disables clipping. */
 typedef struct FbsnnAdam {
   double lr, beta1, beta2, eps, max_grad_norm;
+  double skip_nonfinite;   /* != 0: an iteration whose gradient norm is NaN/inf leaves parameters, moments and the
+                              Adam step counter untouched (heston_dnnpde.py:408-410 skips NaN-loss iterations) */
 } FbsnnAdam;
 
 const char* fbsnn_last_error(void);
@@ -115,7 +126,7 @@ int fbsnn_loss_grad(const FbsnnSpec* spec, const float* params, float* grads, co
 /* clip_grad_norm_ + Adam.step on the flat buffers (with_corr_high_dimension_pde.py:424-425).  `opt_state` is
  * FBSNN_OPT_STATE_BYTES of device memory: int64 step counter at byte 0 (zero-initialised by the caller when the
  * optimizer is created -- the reference builds a fresh Adam per train() call, DeepBSDE.py:272), then float
- * clip_coef @8, step_size @12, sqrt(bias_correction2) @16, grad_norm @20, int64 Philox iteration counter @24 (keep it
+ * clip_coef @8, step_size @12, sqrt(bias_correction2) @16, grad_norm @20, int32 skip flag @32, int64 Philox iteration counter @24 (keep it
  * across optimisers: fbsnn_train_step adds it to `iteration`), and reduction scratch from byte 64.
  * Both counters are advanced on the device, so the call can be replayed from a CUDA graph. */
 #define FBSNN_OPT_STATE_BYTES 2048

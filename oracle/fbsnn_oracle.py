@@ -308,3 +308,104 @@ class OracleSolver:
 def bsb_exact(t, X, T, r=0.05, sigma=0.4):
     """Closed form endorsed by the reference, DeepBSDE.py:345-349."""
     return np.exp((r + sigma ** 2) * (T - t)) * np.sum(X ** 2, axis=-1, keepdims=True)
+
+
+# --------------------------------------------------------------------------------------------
+# Heston 2-factor FBSNN (heston_dnnpde.py:519-659) -- SURVEY.md section 8f row 4
+# --------------------------------------------------------------------------------------------
+class HestonOracle:
+    """Restatement of HestonFBSNN: the base class is built with D = 1 (one Brownian driver, layers[0] inputs), then
+    the input layer(s) are swapped for 3 inputs (t, S, v) and every matrix re-initialised with xavier(gain 0.5),
+    biases zeroed (:533-585) -- same module construction order as the reference, hence the same torch RNG stream."""
+
+    def __init__(self, Xi, T, M, N, layers, mode, activation, kappa=2.0, theta=0.2, sigma=0.3, rho=0.8, v0=0.2,
+                 payoff_type="discontinuous", dtype=torch.float32):
+        self.T, self.M, self.N, self.D = T, M, N, 1
+        self.kappa, self.theta, self.sigma, self.rho, self.v0 = kappa, theta, sigma, rho, v0
+        self.payoff_type, self.strike, self.dtype = payoff_type, 1.0, dtype
+        self.Xi = torch.from_numpy(np.asarray(Xi)).to(dtype)
+        self.Xi.requires_grad = True
+        self.model = build_model(layers, mode, activation)
+        if mode == "FC":
+            self.model[0] = nn.Linear(3, layers[1])
+        else:
+            self.model.layer1 = nn.Linear(3, layers[1])
+            self.model.layer2_input = nn.Linear(3, layers[2])
+            if len(layers) >= 5:
+                self.model.layer3_input = nn.Linear(3, layers[3])
+            if len(layers) == 6:
+                self.model.layer4_input = nn.Linear(3, layers[4])
+        for p in self.model.parameters():
+            if len(p.shape) > 1:
+                nn.init.xavier_uniform_(p, gain=0.5)
+            else:
+                nn.init.zeros_(p)
+        self.model = self.model.to(dtype)
+        self.chol = None
+        self.optimizer = None
+
+    def fetch_minibatch(self):
+        t, W = fetch_minibatch(self.M, self.N, 1, self.T, np.eye(1))      # :309-343 (Cholesky of the 1x1 identity)
+        return t.to(self.dtype), W.to(self.dtype)
+
+    def g_tf(self, S):
+        if self.payoff_type == "discontinuous":
+            return torch.maximum(S - self.strike, torch.tensor(0.0, dtype=S.dtype))
+        return (S - self.strike) / (1 + torch.exp(-10.0 * (S - self.strike)))
+
+    def net_u(self, t, X):
+        S, v = X[:, 0:1], X[:, 1:2]
+        u = torch.clamp(self.model(torch.cat((t, S, v), dim=1)), min=0.0)
+        Du = torch.autograd.grad(u, (S, v), grad_outputs=torch.ones_like(u), create_graph=True, retain_graph=True)
+        return u, Du[0], Du[1]
+
+    def mu_tf(self, X):
+        S, v = X[:, 0:1], X[:, 1:2]
+        return torch.cat([0.05 * S, self.kappa * (self.theta - v)], dim=1).clamp(-100, 100)
+
+    def sigma_tf(self, X):
+        S, v = X[:, 0:1], X[:, 1:2]
+        sS = torch.sqrt(torch.clamp(v, min=1e-8)) * S
+        sv = self.sigma * torch.sqrt(torch.clamp(v, min=1e-8))
+        m = torch.zeros((S.shape[0], 2, 2), dtype=X.dtype)
+        m[:, 0, 0] = sS.squeeze()
+        m[:, 1, 1] = sv.squeeze()
+        m[:, 0, 1] = self.rho * sv.squeeze()
+        m[:, 1, 0] = self.rho * sS.squeeze()
+        return m.clamp(-100, 100)
+
+    def loss_function(self, t, W, Xi=None, return_Z=False):
+        Xi = self.Xi if Xi is None else Xi
+        M = t.shape[0]
+        loss = 0
+        Xs, Ys, Zs = [], [], []
+        t0, W0 = t[:, 0, :], W[:, 0, :]
+        S0 = Xi[:, 0:1].repeat(M, 1) if Xi.shape[0] == 1 else Xi[:, 0:1]
+        X0 = torch.cat([S0, torch.full((M, 1), self.v0, dtype=S0.dtype)], dim=1)
+        Y0, ZS0, Zv0 = self.net_u(t0, X0)
+        Xs.append(X0), Ys.append(Y0), Zs.append(torch.cat([ZS0, Zv0], 1))
+        for n in range(self.N):
+            t1, W1 = t[:, n + 1, :], W[:, n + 1, :]
+            dW = W1 - W0
+            sig = self.sigma_tf(X0)
+            X1 = X0 + self.mu_tf(X0) * (t1 - t0) + torch.einsum('mij,mj->mi', sig, dW)   # dW (M,1) broadcasts over j
+            Y1_tilde = Y0 + 0.05 * Y0 * (t1 - t0) + torch.sum(
+                ZS0 * torch.sum(sig[:, 0, :] * dW, dim=1, keepdim=True) +
+                Zv0 * torch.sum(sig[:, 1, :] * dW, dim=1, keepdim=True), dim=1, keepdim=True)
+            Y1, ZS1, Zv1 = self.net_u(t1, X1)
+            loss = loss + torch.sum((Y1 - Y1_tilde) ** 2)
+            t0, W0, X0, Y0, ZS0, Zv0 = t1, W1, X1, Y1, ZS1, Zv1
+            Xs.append(X0), Ys.append(Y0), Zs.append(torch.cat([ZS0, Zv0], 1))
+        S1 = X1[:, 0:1]
+        gT = self.g_tf(S1)
+        DgT = torch.autograd.grad(gT, S1, grad_outputs=torch.ones_like(gT), allow_unused=True, retain_graph=True,
+                                  create_graph=True)[0]
+        loss = loss + torch.sum((Y1 - self.g_tf(X1[:, 0:1])) ** 2) + torch.sum((ZS1 - DgT) ** 2)
+        X, Y = torch.stack(Xs, dim=1), torch.stack(Ys, dim=1)
+        if return_Z:
+            return loss, X, Y, Y[0, 0, 0], torch.stack(Zs, dim=1)
+        return loss, X, Y, Y[0, 0, 0]
+
+    make_optimizer = OracleSolver.make_optimizer
+    train_step = OracleSolver.train_step
+    grads = OracleSolver.grads

@@ -76,6 +76,13 @@ CASES = [
     dict(name="hjb20_nais_tanh_4l", file="hjb_implement.py", cls="HamiltonJacobiBellman", arity="short",
          problem="hjb", D=20, M=16, N=10, layers=[21, 64, 64, 1], mode="Naisnet", act="Tanh",
          xi="zeros", corr=None, K=3, lr=1e-3, clip=1.0),
+    # Heston 2-factor FBSNN (heston_dnnpde.py:519-659): D = 1 Brownian driver, states (S, v), clip 1.0
+    dict(name="heston_fc_sine", file="heston_dnnpde.py", cls="HestonFBSNN", arity="heston", problem="heston",
+         D=1, M=48, N=20, layers=[2, 64, 64, 64, 1], mode="FC", act="Sine", xi="ones", corr=None, K=4, lr=1e-3,
+         clip=1.0, payoff="discontinuous"),
+    dict(name="heston_nais_tanh_smooth", file="heston_dnnpde.py", cls="HestonFBSNN", arity="heston", problem="heston",
+         D=1, M=16, N=12, layers=[2, 32, 32, 32, 1], mode="Naisnet", act="Tanh", xi="ones", corr=None, K=3, lr=1e-3,
+         clip=1.0, payoff="continuous"),
 ]
 
 TORCH_SEED = 1234
@@ -114,6 +121,9 @@ def run_case(c):
             model = cls(Xi, T, c["M"], c["N"], c["D"], c["layers"], c["mode"], c["act"])
         elif c["arity"] == "mm":
             model = cls(Xi, T, c["M"], c["N"], c["D"], None, c["layers"], c["mode"], c["act"])
+        elif c["arity"] == "heston":
+            model = cls(Xi, T, c["M"], c["N"], c["D"], int(c["N"] ** (1 / 5)), c["layers"], c["mode"], c["act"],
+                        payoff_type=c["payoff"])
         else:
             model = cls(Xi, T, c["M"], c["N"], c["D"], None, c["layers"], c["mode"], c["act"], c["corr"])
     out = {}
@@ -129,9 +139,12 @@ def run_case(c):
     orig_net_u = model.net_u
 
     def spy(t, X):
-        u, du = orig_net_u(t, X)
-        captured.append(du.detach().clone())
-        return u, du
+        res = orig_net_u(t, X)
+        if len(res) == 3:                        # Heston: (u, dU/dS, dU/dv)
+            captured.append(torch.cat([res[1], res[2]], dim=1).detach().clone())
+        else:
+            captured.append(res[1].detach().clone())
+        return res
 
     with contextlib.redirect_stdout(io.StringIO()):
         t_b, W_b = model.fetch_minibatch()

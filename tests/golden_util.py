@@ -65,8 +65,12 @@ def rebuild_inputs(meta, g, squeeze_quirk=True):
     np.random.seed(meta["numpy_seed"])
     D = meta["D"]
     Xi = make_xi(meta["xi"], D)
-    sol = orc.OracleSolver(meta["problem"], Xi, meta["T"], meta["M"], meta["N"], D, meta["layers"],
-                           meta["mode"], meta["act"], squeeze_quirk=squeeze_quirk)
+    if meta["problem"] == "heston":
+        sol = orc.HestonOracle(Xi, meta["T"], meta["M"], meta["N"], meta["layers"], meta["mode"], meta["act"],
+                               payoff_type=meta["payoff"])
+    else:
+        sol = orc.OracleSolver(meta["problem"], Xi, meta["T"], meta["M"], meta["N"], D, meta["layers"],
+                               meta["mode"], meta["act"], squeeze_quirk=squeeze_quirk)
     # the reference with_corr / hjb constructors draw the correlation matrix *after* building the network
     needs_corr = meta["file"] in ("with_corr_high_dimension_pde.py", "hjb_implement.py")
     corr = ref_correlation(meta["corr"], D) if needs_corr else None

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(lib, sym), f"{sym} declared in include/fbsnn_b200.h but not exported"
     assert set(pde._lib.EXPORTS) == declared
-    assert lib.fbsnn_version() == 100
+    assert lib.fbsnn_version() == 101
 
 
 def test_peer_buffer_layout_without_gpu():
@@ -42,7 +42,7 @@ def test_workspace_and_validation_without_gpu():
     lib = pde._lib.load()
     sol = pde.BlackScholesBarenblatt(gu.make_xi("bsb", 100), 1.0, 100, 50, 100, [101] + 4 * [256] + [1], "FC", "Sine")
     sp = sol._spec()
-    assert ctypes.sizeof(sp) == 3 * 4 + 8 * 4 + 6 * 4 + 5 * 4 + 4 + 4 + 4 * 10 * 8 + 8   # matches the C struct
+    assert ctypes.sizeof(sp) == 3 * 4 + 8 * 4 + 6 * 4 + 5 * 4 + 4 + 4 + 4 * 10 * 8 + 8 + 3 * 4 + 5 * 4   # matches the C struct (v101)
     need = ctypes.c_size_t(0)
     assert lib.fbsnn_workspace_bytes(ctypes.byref(sp), 100, 1, ctypes.byref(need)) == 0
     rows = 100 * 51

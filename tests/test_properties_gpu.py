@@ -280,3 +280,47 @@ def test_hjb_cole_hopf_exact_matches_oracle_and_terminal_condition():
     assert abs(got[-1, 0] - g_T) <= 1e-5 * max(1.0, abs(g_T))
     again = pde.hjb_u_exact(t, X, T, MC=400000, seed=9)
     assert np.array_equal(got, again)                                         # Philox: reproducible
+
+
+def test_heston_surface_and_clamp():
+    """HestonFBSNN (heston_dnnpde.py:519-699): (u, dU/dS, dU/dv) outputs with u clamped at 0 and
+    the derivative masked, predict() -> (S, v, Y), train() -> column_stack, in-kernel Brownian driver (1 column)."""
+    from oracle import fbsnn_oracle as orc
+    import dnnpde_b200 as pde
+    torch.manual_seed(4)
+    np.random.seed(4)
+    layers = [2, 32, 32, 32, 1]
+    Xi = np.array([[1.0]])
+    oracle = orc.HestonOracle(Xi, 1.0, 24, 8, layers, "FC", "Sine")
+    tq = torch.rand(50, 1)
+    Xq = torch.cat([0.5 + torch.rand(50, 1), 0.05 + 0.4 * torch.rand(50, 1)], 1).requires_grad_(True)
+    with torch.no_grad():                                                    # centre the raw output on the clamp
+        raw = oracle.model(torch.cat((tq, Xq), 1))
+        oracle.model[-1].bias -= raw.median()
+    sol = pde.HestonFBSNN(Xi, 1.0, 24, 8, 1, 1, layers, "FC", "Sine", precision="fp32")
+    sol.model.load_state_dict(oracle.model.state_dict())
+    ou, oS, ov = oracle.net_u(tq, Xq)
+    u, dS, dv = sol.net_u(tq, Xq.detach())
+    assert u.shape == (50, 1) and dS.shape == (50, 1) and dv.shape == (50, 1)
+    assert (ou.detach() == 0).any() and (ou.detach() > 0).any(), "test rows must straddle the clamp"
+    assert torch.allclose(u.cpu(), ou.detach(), atol=2e-6) and torch.allclose(dS.cpu(), oS.detach(), atol=2e-5)
+    assert torch.allclose(dv.cpu(), ov.detach(), atol=2e-5)
+    with torch.no_grad():
+        raw = oracle.model(torch.cat((tq, Xq), 1))
+    assert (dS.cpu()[raw < -1e-5] == 0).all() and (dv.cpu()[raw < -1e-5] == 0).all()   # masked where the clamp is active
+    t, W = sol.fetch_minibatch()
+    assert W.shape == (24, 9, 1)
+    S, v, Y = sol.predict(Xi, t, W)
+    ol, oX, oY, _ = oracle.loss_function(t.cpu(), W.cpu())
+    assert S.shape == (24, 9, 1) and v.shape == (24, 9, 1) and Y.shape == (24, 9, 1)
+    assert torch.allclose(torch.cat([S, v], 2).cpu(), oX.detach(), atol=1e-6)
+    assert torch.allclose(Y.cpu(), oY.detach(), atol=5e-6)
+    out = sol.train(3, 1e-3)
+    assert out.shape == (1, 3) and out[0, 0] == 0                            # (iteration, mean loss, Y0) rows
+    philox = pde.HestonFBSNN(Xi, 1.0, 512, 8, 1, 1, layers, "FC", "Sine", precision="fp32", brownian="philox",
+                             payoff_type="continuous")
+    philox.train(20, 1e-3)
+    assert np.isfinite(philox.last_losses).all()
+    t2, W2 = philox.fetch_minibatch_device(seed=3)
+    inc = (W2[:, 1:] - W2[:, :-1]).reshape(-1)
+    assert W2.shape == (512, 9, 1) and abs(float(inc.std()) - math.sqrt(1 / 8)) < 0.02

@@ -79,6 +79,44 @@ __device__ __forceinline__ void act_ga(int act, float z, float& g, float& a) {
     a = 1.f - g * g;
   }
 }
+// four elements at once: ONE dispatch on the (warp-uniform) activation code, then four independent evaluations the
+// scheduler can interleave -- the fused epilogues are latency-bound on exactly this chain
+__device__ __forceinline__ void act_ga4(int act, const float z[4], float g[4], float a[4]) {
+  switch (act) {
+    case kActSineCW:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sincos_cw(z[i], g[i], a[i]);
+      break;
+    case kActSineFast:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float k = rintf(z[i] * 0.15915494309189535f);
+        float r = fmaf(-k, 6.2831854820251465f, z[i]);
+        r = fmaf(-k, -1.7484555e-7f, r);
+        g[i] = __sinf(r);
+        a[i] = __cosf(r);
+      }
+      break;
+    case FBSNN_ACT_RELU:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i] = fmaxf(z[i], 0.f), a[i] = z[i] > 0.f ? 1.f : 0.f;
+      break;
+    case kActTanhFast:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        asm("tanh.approx.f32 %0, %1;" : "=f"(g[i]) : "f"(z[i]));
+        a[i] = 1.f - g[i] * g[i];
+      }
+      break;
+    case FBSNN_ACT_SINE:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sincosf(z[i], &g[i], &a[i]);
+      break;
+    default:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i] = tanhf(z[i]), a[i] = 1.f - g[i] * g[i];
+  }
+}
 // second derivative from (g, a): sine -g, relu 0, tanh -2 g a
 __device__ __forceinline__ float act_c(int act, float g, float a) {
   if (act == FBSNN_ACT_SINE || act == kActSineFast || act == kActSineCW) return -g;

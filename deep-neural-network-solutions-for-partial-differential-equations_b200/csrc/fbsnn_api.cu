@@ -435,11 +435,16 @@ static int run_loss(const FbsnnSpec* s, const Plan& p, float* ws, bool with_grad
   a.ev = ws + p.ev, a.part = ws + p.part_loss;
   a.ybar = with_grad ? ws + p.ybar : nullptr, a.V = with_grad ? ws + p.V : nullptr;
   a.umask = s->clamp_u ? ws + p.umask : nullptr;
-  loss_residual_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a);
-  LAUNCH_CHECK("loss_residual");
-  if (with_grad) {
-    loss_seed_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a);
-    LAUNCH_CHECK("loss_seed");
+  if (with_grad && s->D <= 128) {   // fused single pass, one warp per path
+    loss_path_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a, p.rows / (s->N + 1));
+    LAUNCH_CHECK("loss_path");
+  } else {
+    loss_residual_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a);
+    LAUNCH_CHECK("loss_residual");
+    if (with_grad) {
+      loss_seed_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a);
+      LAUNCH_CHECK("loss_seed");
+    }
   }
   final_sum2_kernel<<<1, 1024, 0, st>>>(ws + p.part_loss, p.loss_blocks, FinalSum2{loss_out, with_grad ? ybsum_out : nullptr});
   LAUNCH_CHECK("final_sum2");

@@ -84,8 +84,7 @@ struct EpiFwdT {
     }
     const float z[4] = {v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w};
     float gv[4], av[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) act_ga(act, z[i], gv[i], av[i]);
+    act_ga4(act, z, gv, av);
     const size_t o = (size_t)r * ld + c;
     st4(g + o, make_float4(gv[0], gv[1], gv[2], gv[3]));
     st4(a + o, make_float4(av[0], av[1], av[2], av[3]));

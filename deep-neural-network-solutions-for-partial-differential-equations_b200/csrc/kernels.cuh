@@ -394,6 +394,120 @@ __global__ void loss_seed_kernel(const ProblemK p, const LossArgs a) {
   if (threadIdx.x == 0) a.part[gridDim.x + blockIdx.x] = tot;
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Fused residual + seeds (training, D <= 128): one warp walks ONE PATH through its N+1 rows in order, so the
+// residual e_{n-1} that the seed of row n needs is still in a register -- xin, zf and sdw are read once instead
+// of twice and the ev[] round trip disappears.  The next row's operands are loaded before the current row's
+// warp reductions (two rows in flight per warp).  Same arithmetic as the two kernels above.
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_path_kernel(const ProblemK p, const LossArgs a, long long n_paths) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31;
+  const int N = p.N, D = p.D, ldx = p.ldx;
+  float contrib = 0.f, ybsum = 0.f;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const bool first = g_is_first(p);
+  const bool mulx = p.g_kind == FBSNN_G_SUMSQ || p.g_kind == FBSNN_G_LOGQ;
+  for (long long m = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; m < n_paths; m += wstride) {
+    const long long row0 = m * (N + 1);
+    float xc[4], zc[4], sc[4], xn[4], zn[4], sn[4];
+    auto load_row = [&](long long r, bool with_sd, float* x, float* z, float* sd) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = lane + 32 * j;
+        const bool ok = d < D;
+        x[j] = ok ? a.xin[r * ldx + 1 + d] : 0.f;
+        z[j] = ok ? a.zf[r * ldx + 1 + d] : 0.f;
+        sd[j] = (ok && with_sd) ? a.sdw[r * D + d] : 0.f;
+      }
+    };
+    load_row(row0, N > 0, xc, zc, sc);
+    float t_cur = a.xin[row0 * ldx], y_cur = a.Y[row0], e_prev = 0.f;
+    for (int n = 0; n <= N; ++n) {
+      const long long r = row0 + n;
+      float t_next = 0.f, y_next = 0.f;
+      if (n < N) {
+        load_row(r + 1, n + 1 < N, xn, zn, sn);
+        t_next = a.xin[(r + 1) * ldx], y_next = a.Y[r + 1];
+      }
+      float e, yb;
+      float vrow[4];
+      if (n < N) {
+        float zs = 0.f, xz = 0.f, z2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) zs = fmaf(zc[j], sc[j], zs), xz = fmaf(xc[j], zc[j], xz), z2 = fmaf(zc[j], zc[j], z2);
+        zs = warp_sum(zs), xz = warp_sum(xz), z2 = warp_sum(z2);
+        const float dt = t_next - t_cur;
+        float phi;
+        if (p.phi_kind == FBSNN_PHI_BSB) phi = p.phi_c * (y_cur - xz);
+        else if (p.phi_kind == FBSNN_PHI_RY) phi = p.phi_c * y_cur;
+        else phi = z2;
+        e = y_next - (y_cur + phi * dt + zs);
+        contrib += e * e;
+        const float phi_y = p.phi_kind == FBSNN_PHI_ZSQ ? 0.f : p.phi_c;
+        yb = -2.f * e * (1.f + phi_y * dt);
+        if (n > 0) yb += 2.f * e_prev;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float pz;
+          if (p.phi_kind == FBSNN_PHI_BSB) pz = -p.phi_c * xc[j];
+          else if (p.phi_kind == FBSNN_PHI_RY) pz = 0.f;
+          else pz = 2.f * zc[j];
+          vrow[j] = -2.f * e * (pz * dt + sc[j]);
+        }
+      } else {
+        float sx = 0.f, sx2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sx += xc[j], sx2 = fmaf(xc[j], xc[j], sx2);
+        sx = warp_sum(sx), sx2 = warp_sum(sx2);
+        float g, dgs;
+        if (first) terminal_g_first(p, __shfl_sync(0xffffffffu, xc[0], 0), g, dgs);
+        else terminal_g(p, sx, sx2, g, dgs);
+        float zt = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int d = lane + 32 * j;
+          const float dg = first ? (d == 0 ? dgs : 0.f) : (mulx ? dgs * xc[j] : dgs);
+          const float diff = zc[j] - dg;
+          const bool in = d < p.zt_dims;
+          if (in) zt = fmaf(diff, diff, zt);
+          vrow[j] = in ? 2.f * diff : 0.f;
+        }
+        zt = warp_sum(zt);
+        e = y_cur - g;
+        contrib += e * e + zt;
+        yb = 2.f * e + (N > 0 ? 2.f * e_prev : 0.f);
+      }
+      if (a.umask) {
+        const float mk = a.umask[r];
+        yb *= mk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vrow[j] *= mk;
+      }
+      float* v = a.V + r * ldx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = lane + 32 * j;
+        if (d < D) v[1 + d] = vrow[j];
+      }
+      if (lane == 0) {
+        v[0] = 0.f;
+        a.ybar[r] = yb;
+        ybsum += yb;
+      }
+      for (int c = D + 1 + lane; c < ldx; c += 32) v[c] = 0.f;
+      e_prev = e;
+      t_cur = t_next, y_cur = y_next;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xc[j] = xn[j], zc[j] = zn[j], sc[j] = sn[j];
+    }
+  }
+  // contrib is warp-uniform (every lane holds the reduced values): count it once per warp
+  const float tot = block_sum(lane == 0 ? contrib : 0.f, red);
+  const float tys = block_sum(lane == 0 ? ybsum : 0.f, red);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = tot, a.part[gridDim.x + blockIdx.x] = tys;
+}
+
 // out_j[0] = (float) sum_i part[j*n + i], j = 0,1   (single block, double accumulation, deterministic)
 struct FinalSum2 {
   float* out0;

@@ -6,10 +6,12 @@
 // followed by the weight-gradient contractions G.  tests/passes_model.py states the same algebra on the host.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "kernels.cuh"
 
 namespace fbsnn {
@@ -228,6 +230,32 @@ static bool uses_tc(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
   return s->precision != FBSNN_PREC_FP32 && tc_eligible<A_KC, B_KC>(g, nsplit);
 }
 
+// 3xTF32 weight-gradient contractions go to the CTA-pair (cta_group::2) kernel: measured 4.2 vs 5.2 ms per launch at
+// M = 65 536 (they are shared-memory-bandwidth bound on one CTA).  The sweeps stay on the single-CTA kernel: their
+// k-blocks carry 2-3x fewer MMA cycles, so the pair's longer stage hand-off (remote barrier arrivals) is exposed and
+// they measured 4.4-5.0 vs 3.0-3.9 ms (profiles/r01_launch_table_tf32x3_pair_all.txt).  FBSNN_PAIR=0 disables the
+// pair kernel, FBSNN_PAIR=2 sends every eligible 3xTF32 launch to it (A/B measurements).
+static int pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("FBSNN_PAIR");
+    mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return mode;
+}
+template <bool A_KC, bool B_KC>
+static bool uses_pair(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
+  const int mode = pair_mode();
+  return s->precision == FBSNN_PREC_TF32X3 && (mode == 2 || (mode == 1 && !A_KC)) && tc2_eligible<A_KC, B_KC>(g, nsplit);
+}
+// CTAs of the tcgen05 launch dense() will make for (g, nsplit): the fused bias-gradient partials are per CTA
+template <bool A_KC, bool B_KC>
+static int tc_launch_grid(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
+  if (uses_pair<A_KC, B_KC>(s, g, nsplit)) return tc2_grid(g, nsplit, num_sms());
+  const long long work = (long long)((g.M + tc::BM - 1) / tc::BM) * ((g.N + 255) / 256) * nsplit;
+  return (int)std::min<long long>(work, num_sms());
+}
+
 // dense layer dispatch: SIMT fp32, or tcgen05 TF32 when the variant is selected and the shape qualifies
 template <bool A_KC, bool B_KC, class Epi>
 static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nsplit, cudaStream_t st, const char* what,
@@ -263,8 +291,11 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
         g2.seg[g2.nseg] = g.seg[i], g2.seg[g2.nseg].B = w->lo, g2.mode[g2.nseg++] = 2;
       }
     }
-    if (presplit) e = launch_gemm_tc<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st);
-    else e = launch_gemm_tc<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st);
+    const bool pair = uses_pair<A_KC, B_KC>(s, g, nsplit);
+    if (presplit) e = pair ? launch_gemm_tc2<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st)
+                           : launch_gemm_tc<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st);
+    else e = pair ? launch_gemm_tc2<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st)
+                  : launch_gemm_tc<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st);
   } else {
     e = launch_gemm_tc<A_KC, B_KC, 0>(g, epi, nsplit, num_sms(), st);
   }
@@ -470,7 +501,7 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
   const int col_slots = std::max(p.col_blocks, 256);
   auto col_part = [&](int job) { return ws + p.part_col + (size_t)job * col_slots * 1024; };   // job l = bias of layer l
   bool fused_bias[kMaxL + 2] = {};
-  const int tc_grid = std::min<long long>(num_sms(), (p.rows + 127) / 128);
+  int fused_grid[kMaxL + 2] = {};
   // ---- T sweep -----------------------------------------------------------------------------------------
   for (int l = 1; l <= p.L; ++l) {
     GemmArgs g{};
@@ -492,7 +523,8 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     e.hd = ws + p.hd[l];
     if (l == p.L) {
       e.ybar = ws + p.ybar, e.wout = n.wout;
-      if (uses_tc<true, true>(s, g, 1)) e.colpart = col_part(l), fused_bias[l] = true;   // bias_L gradient fused
+      if (uses_tc<true, true>(s, g, 1))   // bias_L gradient fused
+        e.colpart = col_part(l), fused_bias[l] = true, fused_grid[l] = tc_launch_grid<true, true>(s, g, 1);
     }
     e.ld = p.H[l];
     int rc = p.nais ? dense<true, true>(s, g, e, 1, st, "T") : dense<true, true>(s, g, narrow<EpiTanT>(e), 1, st, "T");
@@ -510,7 +542,8 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
       e.hb_out = (l - 1 >= 2) ? ws + p.hb[l - 1] : nullptr;
     }
     e.ld = p.H[l - 1];
-    if (uses_tc<true, false>(s, g, 1)) e.colpart = col_part(l - 1), fused_bias[l - 1] = true;
+    if (uses_tc<true, false>(s, g, 1))
+      e.colpart = col_part(l - 1), fused_bias[l - 1] = true, fused_grid[l - 1] = tc_launch_grid<true, false>(s, g, 1);
     int rc = p.nais ? dense<true, false>(s, g, e, 1, st, "B") : dense<true, false>(s, g, narrow<EpiBwdT>(e), 1, st, "B");
     if (rc) return rc;
   }
@@ -551,7 +584,7 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     j.B = nullptr, j.y = nullptr;
     j.out = grads + s->off_b[l];
     j.out2 = (p.nais && l >= 2) ? grads + s->off_bin[l] : nullptr;
-    j.part = col_part(l), j.nblk = fused_bias[l] ? tc_grid : p.col_blocks;
+    j.part = col_part(l), j.nblk = fused_bias[l] ? fused_grid[l] : p.col_blocks;
     j.ld = p.H[l], j.width = p.H[l];
     maxw = std::max(maxw, p.H[l]);
   }
@@ -713,7 +746,13 @@ int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const 
   if (use_tc) {
     bool ok = a_kc && b_kc ? tc_eligible<true, true>(g, 1) : (a_kc ? tc_eligible<true, false>(g, 1) : tc_eligible<false, false>(g, 1));
     if (!ok || (!a_kc && b_kc)) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
-    if (use_tc == 2) {
+    if (use_tc == 3) {   // CTA-pair kernel, both operands split in-kernel
+      bool ok2 = a_kc && b_kc ? tc2_eligible<true, true>(g, 1) : (a_kc ? tc2_eligible<true, false>(g, 1) : tc2_eligible<false, false>(g, 1));
+      if (!ok2) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the CTA-pair tcgen05 kernel");
+      if (a_kc && b_kc) err = launch_gemm_tc2<true, true, 2>(g, e, 1, num_sms(), st);
+      else if (a_kc) err = launch_gemm_tc2<true, false, 2>(g, e, 1, num_sms(), st);
+      else err = launch_gemm_tc2<false, false, 2>(g, e, 1, num_sms(), st);
+    } else if (use_tc == 2) {
       if (a_kc && b_kc) err = launch_gemm_tc<true, true, 2>(g, e, 1, num_sms(), st);
       else if (a_kc) err = launch_gemm_tc<true, false, 2>(g, e, 1, num_sms(), st);
       else err = launch_gemm_tc<false, false, 2>(g, e, 1, num_sms(), st);

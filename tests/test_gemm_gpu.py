@@ -63,3 +63,17 @@ def test_tcgen05_3xtf32_gemm_is_fp32_grade(a_kc, b_kc, M, N, K):
     assert torch.isfinite(C).all()
     err = (C.double() - ref).abs()
     assert (err <= 2e-6 * bound + 1e-6).all(), float((err / (bound + 1e-9)).max())
+
+
+@pytest.mark.parametrize("a_kc,b_kc", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (128, 256, 64), (300, 256, 256), (5100, 128, 256), (700, 64, 96),
+                                   (40000, 256, 128), (100000, 192, 256)])
+def test_tcgen05_cta_pair_gemm_is_fp32_grade(a_kc, b_kc, M, N, K):
+    """cta_group::2 form of the 3xTF32 kernel (two CTAs on one 256-row UMMA tile, half of B staged per CTA): same
+    fp32-grade bound, ragged row counts (last pair half empty) and every column count the sweeps use."""
+    if not a_kc:
+        M, K = 256, max(K, 1000 if K == 256 else K) + (7 if K == 128 else 0)   # weight gradients: out = 256, K = rows
+    C, ref, bound = run_gemm(a_kc, b_kc, 3, M, N, K)
+    assert torch.isfinite(C).all()
+    err = (C.double() - ref).abs()
+    assert (err <= 2e-6 * bound + 1e-6).all(), float((err / (bound + 1e-9)).max())

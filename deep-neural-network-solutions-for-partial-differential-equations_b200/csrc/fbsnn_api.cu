@@ -233,8 +233,10 @@ static bool uses_tc(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
 // 3xTF32 weight-gradient contractions go to the CTA-pair (cta_group::2) kernel: measured 4.2 vs 5.2 ms per launch at
 // M = 65 536 (they are shared-memory-bandwidth bound on one CTA).  The sweeps stay on the single-CTA kernel: their
 // k-blocks carry 2-3x fewer MMA cycles, so the pair's longer stage hand-off (remote barrier arrivals) is exposed and
-// they measured 4.4-5.0 vs 3.0-3.9 ms (profiles/r01_launch_table_tf32x3_pair_all.txt).  FBSNN_PAIR=0 disables the
-// pair kernel, FBSNN_PAIR=2 sends every eligible 3xTF32 launch to it (A/B measurements).
+// they measured 4.4-5.0 vs 3.0-3.9 ms (profiles/r01_launch_table_tf32x3_pair_all.txt); with W_hi / W_lo twins in one
+// stage (SPLIT = 3) the pair ties the single-CTA kernel (3.3-3.9 ms, ..._pair_split3_all.txt) -- the sweeps are bound
+// by HBM and the epilogue's load latency, not by shared memory.  FBSNN_PAIR=0 disables the pair kernel, FBSNN_PAIR=2
+// sends every eligible 3xTF32 launch to it (A/B measurements).
 static int pair_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -292,7 +294,15 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
       }
     }
     const bool pair = uses_pair<A_KC, B_KC>(s, g, nsplit);
-    if (presplit) e = pair ? launch_gemm_tc2<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st)
+    if (presplit && pair && g.nseg <= 4) {   // pair sweeps: W_hi / W_lo twins in one stage (SPLIT = 3)
+      GemmArgs g3 = g;
+      for (int i = 0; i < g.nseg; ++i) {
+        const SplitW* w = find_split(g.seg[i].B);
+        g3.seg[i].B = w->hi;
+        g3.seg[i + 4] = g.seg[i], g3.seg[i + 4].B = w->lo;
+      }
+      e = launch_gemm_tc2<A_KC, B_KC, 3>(g3, epi, nsplit, num_sms(), st);
+    } else if (presplit) e = pair ? launch_gemm_tc2<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st)
                            : launch_gemm_tc<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st);
     else e = pair ? launch_gemm_tc2<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st)
                   : launch_gemm_tc<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st);
@@ -746,7 +756,21 @@ int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const 
   if (use_tc) {
     bool ok = a_kc && b_kc ? tc_eligible<true, true>(g, 1) : (a_kc ? tc_eligible<true, false>(g, 1) : tc_eligible<false, false>(g, 1));
     if (!ok || (!a_kc && b_kc)) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
-    if (use_tc == 3) {   // CTA-pair kernel, both operands split in-kernel
+    if (use_tc == 4) {   // CTA-pair kernel, B pre-split into exact-TF32 hi / lo twins (the sweeps' form); test hook only
+      if (!a_kc) return fail(FBSNN_E_UNSUPPORTED, "pre-split B is the sweeps' form (A k-contiguous)");
+      if (!(b_kc ? tc2_eligible<true, true>(g, 1) : tc2_eligible<true, false>(g, 1)))
+        return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the CTA-pair tcgen05 kernel");
+      const int nb = b_kc ? N * ldb : K * ldb;
+      float* hl = nullptr;
+      if (cudaMalloc(&hl, 2 * (size_t)nb * sizeof(float)) != cudaSuccess) return fail(FBSNN_E_CUDA, "cudaMalloc");
+      split_hi_lo_kernel<<<(nb + 255) / 256, 256, 0, st>>>(B, nb, hl, hl + nb);
+      GemmArgs g3 = g;
+      g3.seg[0].B = hl;
+      g3.seg[4] = g.seg[0], g3.seg[4].B = hl + nb;
+      err = b_kc ? launch_gemm_tc2<true, true, 3>(g3, e, 1, num_sms(), st) : launch_gemm_tc2<true, false, 3>(g3, e, 1, num_sms(), st);
+      cudaStreamSynchronize(st);
+      cudaFree(hl);
+    } else if (use_tc == 3) {   // CTA-pair kernel, both operands split in-kernel
       bool ok2 = a_kc && b_kc ? tc2_eligible<true, true>(g, 1) : (a_kc ? tc2_eligible<true, false>(g, 1) : tc2_eligible<false, false>(g, 1));
       if (!ok2) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the CTA-pair tcgen05 kernel");
       if (a_kc && b_kc) err = launch_gemm_tc2<true, true, 2>(g, e, 1, num_sms(), st);

@@ -21,7 +21,11 @@
 //              the LEADER's tempty[acc] (count = 2 x 8)
 // TMEM is allocated with tcgen05.alloc.cta_group::2 by warp 1 of both CTAs; cluster barriers bracket set-up and
 // tear-down so that no CTA touches (or leaves) a peer whose barriers are not live.
-// Only SPLIT in {1, 2} is built: single-pass TF32 is not shared-memory bound.
+// SPLIT = 1, 2 as in gemm_tc.cuh; SPLIT = 3 (sweeps on the pair): the weight operand has exact-TF32 hi / lo twins in
+// global memory (seg[s].B = W_hi, seg[s + 4].B = W_lo) which TMA drops into the B and B_lo slots of ONE stage, only A is
+// split in-kernel, three MMAs per k-step -- the A tile is fetched once (SPLIT = 1 fetches it for the hi and again for
+// the lo segment) and a stage carries 1536 MMA cycles, which covers the pair's stage hand-off latency.
+// Single-pass TF32 is not shared-memory bound and has no pair form.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -34,14 +38,14 @@ constexpr int B_HALF_BYTES = 128 * BK * 4;   // 16 KB: at most 128 of the 256 B 
 
 template <int SPLIT>
 struct Cfg2 {
-  static_assert(SPLIT == 1 || SPLIT == 2, "the CTA-pair kernel exists for the 3xTF32 variants only");
-  static constexpr int STAGES = SPLIT == 2 ? 3 : 4;
+  static_assert(SPLIT >= 1 && SPLIT <= 3, "the CTA-pair kernel exists for the 3xTF32 variants only");
+  static constexpr int STAGES = SPLIT >= 2 ? 3 : 4;
   static constexpr int SPLIT_WARPS = 4;
   static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
   static constexpr int SPLIT_TEAM_WARPS = SPLIT == 2 ? SPLIT_WARPS + NUM_EPI_WARPS : SPLIT_WARPS;
   static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
   // [A 16K][B 16K][A_lo 16K]([B_lo 16K])
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES + A_STAGE_BYTES + (SPLIT == 2 ? B_HALF_BYTES : 0);
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES + A_STAGE_BYTES + (SPLIT >= 2 ? B_HALF_BYTES : 0);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES + 1024 /*align*/ + 256;
 };
 
@@ -157,7 +161,7 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
     // ===================== TMA producer (own rows of A, own half of B) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t bytes = A_STAGE_BYTES + (uint32_t)NH * BK * 4;
+      const uint32_t bytes = A_STAGE_BYTES + (uint32_t)NH * BK * 4 * (SPLIT == 3 ? 2 : 1);
       for (int w = cid; w < num_work; w += ncl) {
         const int mt2 = w % num_mtiles2, split = w / num_mtiles2;
         const int m0 = mt2 * 256 + 128 * (int)rank, n0 = NH * (int)rank;
@@ -177,6 +181,14 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
               for (int c = 0; c < NH / 32; ++c) tma_load_2d(b + c * 4096, &tm.b[s], &full[stage], n0 + 32 * c, k0);
             } else {
               tma_load_2d(b, &tm.b[s], &full[stage], k0, n0);
+            }
+            if (SPLIT == 3) {   // W_lo twin -> the B_lo slot
+              uint8_t* bl = b + B_HALF_BYTES + A_STAGE_BYTES;
+              if (B_MN) {
+                for (int c = 0; c < NH / 32; ++c) tma_load_2d(bl + c * 4096, &tm.b[s + 4], &full[stage], n0 + 32 * c, k0);
+              } else {
+                tma_load_2d(bl, &tm.b[s + 4], &full[stage], k0, n0);
+              }
             }
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
@@ -202,7 +214,7 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
             const uint32_t a = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t b = a + A_STAGE_BYTES;
             const uint32_t alo = b + B_HALF_BYTES, blo = alo + A_STAGE_BYTES;
-            const int mode = SPLIT == 2 ? 3 : g.mode[s];
+            const int mode = SPLIT >= 2 ? 3 : g.mode[s];
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               auto da = [&](uint32_t base) { return A_MN ? make_desc(base + k * 1024, 4096, 512, 1) : make_desc(base + k * 32, 16, 1024, 2); };
@@ -211,7 +223,7 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
                 umma_tf32_pair(tmem_d, da(alo), db(b), idesc, first ? 0u : 1u);
                 first = 0;
               }
-              if (SPLIT == 2) umma_tf32_pair(tmem_d, da(a), db(blo), idesc, 1u);
+              if (SPLIT >= 2) umma_tf32_pair(tmem_d, da(a), db(blo), idesc, 1u);
               umma_tf32_pair(tmem_d, da(a), db(b), idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -309,7 +321,7 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
           float4* lo = (float4*)(smem + sstage * C::STAGE_BYTES + A_STAGE_BYTES + B_HALF_BYTES);
           // [A 16K][B 16K] and their lo twins [A_lo 16K][B_lo 16K] are laid out alike; with fewer than 128 B columns
           // per CTA the B tile is shorter but still starts at the 16 KB mark
-          const int n4 = SPLIT == 2 ? nA4 + nB4 : (g.mode[s] == 1 ? nA4 : 0);
+          const int n4 = SPLIT == 2 ? nA4 + nB4 : (SPLIT == 3 || g.mode[s] == 1 ? nA4 : 0);
           for (int i0 = ts; i0 < n4; i0 += TEAM * 8) {
             float4 x[8];
 #pragma unroll
@@ -418,6 +430,16 @@ inline cudaError_t launch_gemm_tc2(const GemmArgs& g, const Epi& epi, int nsplit
     if (!ok) return cudaErrorInvalidValue;
   }
   for (int s = g.nseg; s < kMaxSeg; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];
+  if (SPLIT == 3) {   // lo twins of the weight operands ride in seg[s + 4].B
+    if (g.nseg > 4) return cudaErrorInvalidValue;
+    for (int s = 0; s < g.nseg; ++s) {
+      const GemmSeg& sg = g.seg[s];
+      const float* lo = g.seg[s + 4].B;
+      const bool ok = B_MN ? tc::make_map(&tm.b[s + 4], lo, g.Nb, sg.K, sg.ldb, 32, 32, true)
+                           : tc::make_map(&tm.b[s + 4], lo, sg.K, g.Nb, sg.ldb, 32, NH, false);
+      if (!ok || !lo) return cudaErrorInvalidValue;
+    }
+  }
   auto kern = tc2::gemm_tc2_kernel<A_MN, B_MN, SPLIT, Epi>;
   static bool attr_set = false;
   if (!attr_set) {

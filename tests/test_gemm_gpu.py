@@ -77,3 +77,13 @@ def test_tcgen05_cta_pair_gemm_is_fp32_grade(a_kc, b_kc, M, N, K):
     assert torch.isfinite(C).all()
     err = (C.double() - ref).abs()
     assert (err <= 2e-6 * bound + 1e-6).all(), float((err / (bound + 1e-9)).max())
+
+
+@pytest.mark.parametrize("b_kc", [1, 0])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (300, 256, 256), (5100, 128, 128), (700, 64, 96), (40000, 256, 256)])
+def test_tcgen05_cta_pair_presplit_weights(b_kc, M, N, K):
+    """the sweeps' pair form: W_hi / W_lo twins loaded by TMA into one stage, only A split in-kernel (SPLIT = 3)."""
+    C, ref, bound = run_gemm(1, b_kc, 4, M, N, K)
+    assert torch.isfinite(C).all()
+    err = (C.double() - ref).abs()
+    assert (err <= 2e-6 * bound + 1e-6).all(), float((err / (bound + 1e-9)).max())

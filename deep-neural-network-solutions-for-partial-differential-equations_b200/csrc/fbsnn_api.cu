@@ -400,6 +400,8 @@ static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* 
 static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, bool with_grad, cudaStream_t st) {
   const int R = (int)p.rows;
   int act = s->act_kind;
+  // 3xTF32 keeps the fp32-grade sine (Cody-Waite + minimax polynomials, ~22 instructions): the F-sweep epilogue is
+  // instruction-bound on it (3.3 ms per layer vs 2.8 ms with the MUFU form, measured), the price of fp32-grade results
   if (s->precision == FBSNN_PREC_TF32X3 && act == FBSNN_ACT_SINE) act = kActSineCW;
   if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_SINE) act = kActSineFast;
   if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_TANH) act = kActTanhFast;

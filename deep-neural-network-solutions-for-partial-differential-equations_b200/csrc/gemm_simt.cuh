@@ -48,8 +48,16 @@ template <>
 struct FragT<false> {
   float4 x, y;
 };
+// Per-column constants (biases, output weights) are fetched once per column group with col_prefetch(c) -- the tcgen05
+// epilogue reuses them for the 8 rows a thread handles in a chunk instead of re-loading them per row.
+struct ColNone {};
 #define FBSNN_EPI_CALL                                                                                   \
-  __device__ __forceinline__ void operator()(int r, int c, float4 v) const { finish(r, c, v, prefetch(r, c)); }
+  __device__ __forceinline__ void operator()(int r, int c, float4 v) const {                            \
+    finish(r, c, v, prefetch(r, c), col_prefetch(c));                                                    \
+  }
+#define FBSNN_EPI_NO_COLS                                                                                \
+  typedef ColNone ColFrag;                                                                               \
+  __device__ __forceinline__ ColFrag col_prefetch(int) const { return ColFrag{}; }
 
 // F sweep: z = acc + bias;  g = act(z), a = act'(z);  h = g (+ h_prev);  last layer also seeds the adjoint
 template <bool RES>
@@ -76,12 +84,21 @@ struct EpiFwdT {
     else f.y = make_float4(0.f, 0.f, 0.f, 0.f);
     return f;
   }
-  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
-    float4 b = ld4(bias1 + c);   // small, L1-resident
+  struct ColFrag {
+    float4 b, w;   // bias (sum of both), output weights (last hidden layer)
+  };
+  __device__ __forceinline__ ColFrag col_prefetch(int c) const {
+    ColFrag cf;
+    cf.b = ld4(bias1 + c);
     if (bias2) {
       const float4 b2 = ld4(bias2 + c);
-      b.x += b2.x, b.y += b2.y, b.z += b2.z, b.w += b2.w;
+      cf.b.x += b2.x, cf.b.y += b2.y, cf.b.z += b2.z, cf.b.w += b2.w;
     }
+    cf.w = wout ? ld4(wout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return cf;
+  }
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f, const ColFrag& cf) const {
+    const float4 b = cf.b;
     const float z[4] = {v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w};
     float gv[4], av[4];
     act_ga4(act, z, gv, av);
@@ -90,7 +107,7 @@ struct EpiFwdT {
     st4(a + o, make_float4(av[0], av[1], av[2], av[3]));
     if (RES && h) st4(h + o, make_float4(gv[0] + f.y.x, gv[1] + f.y.y, gv[2] + f.y.z, gv[3] + f.y.w));
     if (wout) {
-      const float4 w = ld4(wout + c);
+      const float4 w = cf.w;
       st4(delta + o, make_float4(w.x * av[0], w.y * av[1], w.z * av[2], w.w * av[3]));
       if (s)
         st4(s + o, make_float4(w.x * act_c(act, gv[0], av[0]), w.y * act_c(act, gv[1], av[1]),
@@ -122,7 +139,8 @@ struct EpiAdjT {
     if constexpr (RES) f.z = res ? ld4(res + o) : (res_head ? ld4(res_head + c) : make_float4(0.f, 0.f, 0.f, 0.f));
     return f;
   }
-  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f) const {
+  FBSNN_EPI_NO_COLS
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag& f, const ColFrag& = ColFrag{}) const {
     const size_t o = (size_t)r * ld + c;
     float ht[4] = {v.x, v.y, v.z, v.w};
     if constexpr (RES) ht[0] += f.z.x, ht[1] += f.z.y, ht[2] += f.z.z, ht[3] += f.z.w;
@@ -158,7 +176,15 @@ struct EpiTanT {
     if constexpr (RES) f.z = res ? ld4(res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
     return f;
   }
-  __device__ __forceinline__ float4 finish(int r, int c, float4 v, const Frag& f) const {
+  struct ColFrag {
+    float4 w;
+  };
+  __device__ __forceinline__ ColFrag col_prefetch(int c) const {
+    ColFrag cf;
+    cf.w = wout ? ld4(wout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return cf;
+  }
+  __device__ __forceinline__ float4 finish(int r, int c, float4 v, const Frag& f, const ColFrag& cf) const {
     const size_t o = (size_t)r * ld + c;
     const float4 av = f.x, sv = f.y;
     float hdv[4] = {v.x * av.x, v.y * av.y, v.z * av.z, v.w * av.w};
@@ -166,7 +192,7 @@ struct EpiTanT {
     float zz[4] = {v.x * sv.x, v.y * sv.y, v.z * sv.z, v.w * sv.w};
     if (wout) {
       const float yb = ybar[r];
-      const float4 w = ld4(wout + c);
+      const float4 w = cf.w;
       zz[0] += yb * w.x * av.x, zz[1] += yb * w.y * av.y, zz[2] += yb * w.z * av.z, zz[3] += yb * w.w * av.w;
     }
     st4(hd + o, make_float4(hdv[0], hdv[1], hdv[2], hdv[3]));
@@ -208,7 +234,8 @@ struct EpiBwdT {
     }
     return f;
   }
-  __device__ __forceinline__ float4 finish(int r, int c, float4 v, const Frag& f) const {
+  FBSNN_EPI_NO_COLS
+  __device__ __forceinline__ float4 finish(int r, int c, float4 v, const Frag& f, const ColFrag& = ColFrag{}) const {
     const size_t o = (size_t)r * ld + c;
     float hb[4] = {v.x, v.y, v.z, v.w};
     if constexpr (RES) hb[0] += f.z.x, hb[1] += f.z.y, hb[2] += f.z.z, hb[3] += f.z.w;
@@ -238,7 +265,10 @@ struct EpiStore {
   int ld;
   int io_arrays() const { return 1; }
   __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
-  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&) const { st4(out + (size_t)r * ld + c, v); }
+  FBSNN_EPI_NO_COLS
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&, const ColFrag& = ColFrag{}) const {
+    st4(out + (size_t)r * ld + c, v);
+  }
   FBSNN_EPI_CALL
 };
 
@@ -250,7 +280,8 @@ struct EpiPartial {
   int M, N;
   int io_arrays() const { return 1; }
   __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
-  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&) const {
+  FBSNN_EPI_NO_COLS
+  __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&, const ColFrag& = ColFrag{}) const {
     st4(out + ((size_t)blockIdx.z * M + r) * N + c, v);
   }
   __device__ __forceinline__ void finish_split(int split, int r, int c, float4 v) const {

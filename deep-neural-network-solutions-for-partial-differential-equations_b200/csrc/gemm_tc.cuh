@@ -305,6 +305,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
                           __uint_as_float(v[4 * j + 3])));
         __syncwarp();
         const int cc = c4 * 4;
+        const typename Epi::ColFrag cf = epi.col_prefetch(c0 + cc);   // biases / output weights of these 4 columns
 #pragma unroll
         for (int ib = 0; ib < 2; ++ib) {
           typename Epi::Frag f[4];
@@ -321,10 +322,10 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
               if constexpr (std::is_same<Epi, EpiPartial>::value) {
                 epi.finish_split(split, r0 + rr, c0 + cc, a4);
               } else if constexpr (kColsum) {
-                const float4 zb = epi.finish(r0 + rr, c0 + cc, a4, f[i]);
+                const float4 zb = epi.finish(r0 + rr, c0 + cc, a4, f[i], cf);
                 cs.x += zb.x, cs.y += zb.y, cs.z += zb.z, cs.w += zb.w;
               } else {
-                epi.finish(r0 + rr, c0 + cc, a4, f[i]);
+                epi.finish(r0 + rr, c0 + cc, a4, f[i], cf);
               }
             }
           }

@@ -272,8 +272,9 @@ def measure_roofline(c, args, sol, batches, ms_per_step, m_loc):
     # rates alongside ("Roofline").
     return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
             "traffic": traffic, "algorithmic_bytes_per_launch": dense_bytes / max(n_dense, 1),
-            "kernel": (f"gemm_tc_kernel (tcgen05 kind::tf32{' x3 hi/lo split' if args.precision == 'tf32x3' else ''}, "
-                       "TMA, TMEM)") if is_tc else "gemm_simt_kernel (fp32 FMA)",
+            "kernel": (("gemm_tc_kernel (tcgen05 kind::tf32 x3 hi/lo split, TMA, TMEM; sweeps) + gemm_tc2_kernel "
+                        "(cta_group::2 pair; weight gradients)") if args.precision == "tf32x3" else
+                       "gemm_tc_kernel (tcgen05 kind::tf32, TMA, TMEM)") if is_tc else "gemm_simt_kernel (fp32 FMA)",
             "launches_per_step": n_dense, "dense_ms_per_step": dense_ms, "dense_share_of_step": dense_ms / ms_per_step,
             "algorithmic_bytes_per_step": dense_bytes, "tflops": tflops, "tf32_peak_tflops": tf32_peak,
             "tensor_frac": tflops / tf32_peak, "tc_launches": int(out[3]) // nrep,

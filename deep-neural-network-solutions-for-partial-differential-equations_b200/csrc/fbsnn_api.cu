@@ -254,8 +254,8 @@ static bool uses_pair(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
 template <bool A_KC, bool B_KC>
 static int tc_launch_grid(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
   if (uses_pair<A_KC, B_KC>(s, g, nsplit)) return tc2_grid(g, nsplit, num_sms());
-  const long long work = (long long)((g.M + tc::BM - 1) / tc::BM) * ((g.N + 255) / 256) * nsplit;
-  return (int)std::min<long long>(work, num_sms());
+  if (s->precision == FBSNN_PREC_TF32X3) return tc_colpart_rows<A_KC, 1>(g, nsplit, num_sms());
+  return tc_colpart_rows<A_KC, 0>(g, nsplit, num_sms());
 }
 
 // dense layer dispatch: SIMT fp32, or tcgen05 TF32 when the variant is selected and the shape qualifies

@@ -419,7 +419,11 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
               const int e2 = half * 4 + ((qq - C::EPI_WARP0) & 3);
               tot += epi_tiles[e2 * (EPI_TILE_BYTES / 4) + c];
             }
-            epi.colpart[(size_t)blockIdx.x * 1024 + half * ncol + c] = tot;
+            // one partial row per CTA -- or per m-tile when every CTA has exactly one work item (narrow column
+            // tiles at small row counts: the column tiles of an m-tile then fill one row between them)
+            const int prow = num_work <= (int)gridDim.x ? (int)(blockIdx.x % num_mtiles) : (int)blockIdx.x;
+            const int pn0 = num_work <= (int)gridDim.x ? (int)((blockIdx.x % num_mn) / num_mtiles) * BN : 0;
+            epi.colpart[(size_t)prow * 1024 + pn0 + half * ncol + c] = tot;
           }
         }
       }
@@ -481,8 +485,40 @@ inline bool tc_eligible(const GemmArgs& g, int nsplit) {
   return true;
 }
 
+// column-tile width for (g, nsplit): 256, or -- for sweeps over few rows, where 128-row x 256-column tiles would leave
+// most SMs idle -- the narrowest of 128 / 64 that still gives every CTA at most one work item
+template <bool A_KC, int SPLIT>
+inline int tc_pick_bn(const GemmArgs& g, int nsplit, int num_sms) {
+  if (!A_KC || SPLIT == 2 || nsplit != 1 || g.N % 128) return 256;
+  const int mtiles = (g.M + tc::BM - 1) / tc::BM;
+  if (g.N == 256 && mtiles * 4 <= num_sms) return 64;
+  if (mtiles * (g.N / 128) <= num_sms && g.N > 128) return 128;
+  return 256;
+}
+// rows of fused column-sum partials the launch writes (see the kernel's colpart indexing)
+template <bool A_KC, int SPLIT>
+inline int tc_colpart_rows(const GemmArgs& g, int nsplit, int num_sms) {
+  const int bn = tc_pick_bn<A_KC, SPLIT>(g, nsplit, num_sms);
+  const int mtiles = (g.M + tc::BM - 1) / tc::BM;
+  const long long work = (long long)mtiles * ((g.N + bn - 1) / bn) * nsplit;
+  return work <= num_sms ? mtiles : num_sms;
+}
+
 template <bool A_KC, bool B_KC, int SPLIT, class Epi, int BN = 256>
+inline cudaError_t launch_gemm_tc_bn(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st);
+
+template <bool A_KC, bool B_KC, int SPLIT, class Epi>
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
+  if constexpr (A_KC && SPLIT != 2) {
+    const int bn = tc_pick_bn<A_KC, SPLIT>(g, nsplit, num_sms);
+    if (bn == 64) return launch_gemm_tc_bn<A_KC, B_KC, SPLIT, Epi, 64>(g, epi, nsplit, num_sms, st);
+    if (bn == 128) return launch_gemm_tc_bn<A_KC, B_KC, SPLIT, Epi, 128>(g, epi, nsplit, num_sms, st);
+  }
+  return launch_gemm_tc_bn<A_KC, B_KC, SPLIT, Epi, 256>(g, epi, nsplit, num_sms, st);
+}
+
+template <bool A_KC, bool B_KC, int SPLIT, class Epi, int BN>
+inline cudaError_t launch_gemm_tc_bn(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
   constexpr bool A_MN = !A_KC, B_MN = !B_KC;
   using C = tc::Cfg<SPLIT, BN>;
   tc::TmSet tm;

@@ -478,7 +478,9 @@ static int run_loss(const FbsnnSpec* s, const Plan& p, float* ws, bool with_grad
   a.ev = ws + p.ev, a.part = ws + p.part_loss;
   a.ybar = with_grad ? ws + p.ybar : nullptr, a.V = with_grad ? ws + p.V : nullptr;
   a.umask = s->clamp_u ? ws + p.umask : nullptr;
-  if (with_grad && s->D <= 128) {   // fused single pass, one warp per path
+  // fused single pass, one warp per path: wins once there are enough paths to hide the row-to-row latency of a
+  // warp's walk (1.5 vs 4.3 ms at M = 65 536); below ~2k paths the row-parallel pair is faster (18 vs 62 us at M = 100)
+  if (with_grad && s->D <= 128 && p.rows / (s->N + 1) >= 2048) {
     loss_path_kernel<<<p.loss_blocks, 256, 0, st>>>(k, a, p.rows / (s->N + 1));
     LAUNCH_CHECK("loss_path");
   } else {

@@ -324,3 +324,39 @@ def test_heston_surface_and_clamp():
     t2, W2 = philox.fetch_minibatch_device(seed=3)
     inc = (W2[:, 1:] - W2[:, :-1]).reshape(-1)
     assert W2.shape == (512, 9, 1) and abs(float(inc.std()) - math.sqrt(1 / 8)) < 0.02
+
+
+@pytest.mark.parametrize("problem", ["bsb", "hjb", "basket", "heston", "heston_smooth"])
+def test_fused_path_loss_kernel_matches_row_parallel_kernels(problem):
+    """From 2048 paths up the residual + seeds run as one per-path kernel (loss_path_kernel); below, as the two
+    row-parallel kernels.  The whole batch (fused kernel) must equal the sum over shards of 1024 paths (row-parallel
+    kernels): loss, gradients, Y -- for every form of phi / g, the Heston clamp mask and the first-component payoffs."""
+    import dnnpde_b200 as pde
+    torch.manual_seed(3)
+    M, Nn = 4096, 12
+    if problem.startswith("heston"):
+        sol = pde.HestonFBSNN(np.array([[1.0]]), 1.0, M, Nn, 1, 1, [2, 64, 64, 1], "FC", "Sine", precision="fp32", seed=9,
+                              payoff_type="continuous" if problem.endswith("smooth") else "discontinuous")
+        with torch.no_grad():
+            sol.model[-1].bias += 0.05                          # straddle the clamp
+    else:
+        Dd = 10
+        cls = {"bsb": pde.BlackScholesBarenblatt, "hjb": pde.HamiltonJacobiBellman, "basket": pde.BasketCallOption}[problem]
+        layers = [Dd + 1, 64, 64, 64, 1]
+        xi = np.zeros((1, Dd)) if problem == "hjb" else np.ones((1, Dd))
+        if problem == "basket":
+            sol = cls(xi, 1.0, M, Nn, Dd, None, layers, "FC", "Tanh", precision="fp32", seed=9)
+        else:
+            sol = cls(xi, 1.0, M, Nn, Dd, layers, "FC", "Sine", precision="fp32", seed=9)
+    t, W = sol.fetch_minibatch_device(iteration=2)
+    loss, X, Y, _, g = sol.loss_grad_flat(t, W)
+    loss, g, Y = float(loss), g.clone(), Y.clone()
+    acc_l, acc_g = 0.0, torch.zeros_like(g)
+    for lo in range(0, M, 1024):
+        sol.M = 1024
+        l, _, Ys, _, gs = sol.loss_grad_flat(t[lo:lo + 1024].contiguous(), W[lo:lo + 1024].contiguous())
+        acc_l += float(l)
+        acc_g += gs
+        assert torch.equal(Ys, Y[lo:lo + 1024])
+    assert np.isfinite(loss) and abs(acc_l - loss) <= 5e-6 * abs(loss), (acc_l, loss)
+    assert float((acc_g - g).abs().max()) <= 5e-5 * float(g.abs().max())

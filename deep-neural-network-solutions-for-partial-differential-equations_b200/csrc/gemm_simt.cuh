@@ -51,6 +51,9 @@ struct FragT<false> {
 // Per-column constants (biases, output weights) are fetched once per column group with col_prefetch(c) -- the tcgen05
 // epilogue reuses them for the 8 rows a thread handles in a chunk instead of re-loading them per row.
 struct ColNone {};
+// l2_prefetch(r, c): pull the 128-byte lines prefetch(r, c) will read into L2 (no registers held while in flight); the
+// tcgen05 epilogue calls it one 32-column chunk ahead -- its stalls are the HBM latency of exactly these loads
+__device__ __forceinline__ void l2_line(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #define FBSNN_EPI_CALL                                                                                   \
   __device__ __forceinline__ void operator()(int r, int c, float4 v) const {                            \
     finish(r, c, v, prefetch(r, c), col_prefetch(c));                                                    \
@@ -78,6 +81,9 @@ struct EpiFwdT {
   int ld, act;
   // number of (rows x N) fp32 arrays this epilogue reads + writes (algorithmic HBM traffic, bench.py roofline)
   int io_arrays() const { return 2 + (h ? 2 : 0) + (wout ? (s ? 2 : 1) : 0); }
+  __device__ __forceinline__ void l2_prefetch(int r, int c) const {
+    if (RES && h) l2_line(res + (size_t)r * ld + c);
+  }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     Frag f;
     if (RES && h) f.y = ld4(res + (size_t)r * ld + c);
@@ -131,6 +137,12 @@ struct EpiAdjT {
   float* s;               // nullable (forward-only mode)
   int ld, act;
   int io_arrays() const { return 2 + (s ? 2 : 0) + (res ? 1 : 0) + (ht_out ? 1 : 0); }
+  __device__ __forceinline__ void l2_prefetch(int r, int c) const {
+    const size_t o = (size_t)r * ld + c;
+    l2_line(a + o);
+    if (s) l2_line(g + o);
+    if (RES && res) l2_line(res + o);
+  }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
     Frag f;
@@ -168,6 +180,12 @@ struct EpiTanT {
   float* colpart;     // nullable: [grid][1024] per-CTA column sums of zbar (last layer), tcgen05 kernel only
   int ld;
   int io_arrays() const { return 4 + (res ? 1 : 0); }
+  __device__ __forceinline__ void l2_prefetch(int r, int c) const {
+    const size_t o = (size_t)r * ld + c;
+    l2_line(a + o);
+    l2_line(s_zz + o);
+    if (RES && res) l2_line(res + o);
+  }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
     Frag f;
@@ -216,6 +234,12 @@ struct EpiBwdT {
   float* colpart;     // nullable: [grid][1024] per-CTA column sums of zbar, tcgen05 kernel only
   int ld;
   int io_arrays() const { return 3 + (res ? 1 : 0) + (hb_out ? 1 : 0); }
+  __device__ __forceinline__ void l2_prefetch(int r, int c) const {
+    const size_t o = (size_t)r * ld + c;
+    l2_line(a + o);
+    l2_line(zz_zbar + o);
+    if (RES && res) l2_line(res + o);
+  }
   __device__ __forceinline__ Frag prefetch(int r, int c) const {
     const size_t o = (size_t)r * ld + c;
     Frag f;
@@ -265,6 +289,7 @@ struct EpiStore {
   int ld;
   int io_arrays() const { return 1; }
   __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
+  __device__ __forceinline__ void l2_prefetch(int, int) const {}
   FBSNN_EPI_NO_COLS
   __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&, const ColFrag& = ColFrag{}) const {
     st4(out + (size_t)r * ld + c, v);
@@ -280,6 +305,7 @@ struct EpiPartial {
   int M, N;
   int io_arrays() const { return 1; }
   __device__ __forceinline__ Frag prefetch(int, int) const { return Frag{}; }
+  __device__ __forceinline__ void l2_prefetch(int, int) const {}
   FBSNN_EPI_NO_COLS
   __device__ __forceinline__ void finish(int r, int c, float4 v, const Frag&, const ColFrag& = ColFrag{}) const {
     st4(out + ((size_t)blockIdx.z * M + r) * N + c, v);

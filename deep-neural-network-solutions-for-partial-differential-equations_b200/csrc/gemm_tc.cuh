@@ -293,6 +293,18 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
       for (int ch = 0; ch * 32 < ncol; ++ch) {
         const int ct = half * ncol + ch * 32;   // column inside the CTA tile (TMEM column)
         const int c0 = n0 + ct;                 // global output column
+        if (c4 == 0) {
+          // the lines this warp's loads touch in the NEXT chunk (or in the first chunk of its next tile) -> L2 now
+          const bool more = (ch + 1) * 32 < ncol;
+          const int wn = w + gridDim.x;
+          if (more || wn < num_work) {
+            const int pr0 = more ? r0 : (wn % num_mtiles) * BM + q * 32;
+            const int pc0 = more ? c0 + 32 : ((wn % num_mn) / num_mtiles) * BN + half * ncol;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (pr0 + 4 * i + sub < g.M) epi.l2_prefetch(pr0 + 4 * i + sub, pc0);
+          }
+        }
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ct;

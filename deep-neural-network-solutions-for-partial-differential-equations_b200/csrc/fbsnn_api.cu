@@ -12,6 +12,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "gemm_tc16.cuh"
 #include "kernels.cuh"
 
 namespace fbsnn {
@@ -237,6 +238,27 @@ static bool uses_tc(const FbsnnSpec* s, const GemmArgs& g, int nsplit) {
 // stage (SPLIT = 3) the pair ties the single-CTA kernel (3.3-3.9 ms, ..._pair_split3_all.txt) -- the sweeps are bound
 // by HBM and the epilogue's load latency, not by shared memory.  FBSNN_PAIR=0 disables the pair kernel, FBSNN_PAIR=2
 // sends every eligible 3xTF32 launch to it (A/B measurements).
+// The F sweep runs on the 16-epilogue-warp form of the tcgen05 kernel (gemm_tc16.cuh): its epilogue is instruction-
+// bound on the sine/cosine (3.0 vs 3.6 ms per layer, 2.2 vs 3.5 ms for the first layer, measured on one box).  The
+// A/T/B sweeps measured SLOWER on it (4.4 / 4.25 / 3.3 vs 3.6 / 3.8 / 2.8 ms: 64-byte row segments and 80 registers
+// hurt their load-bound epilogues) and stay on the 8-warp form.  FBSNN_EPI16=0 disables, =2 sends every sweep to it.
+template <class Epi, class = void>
+struct wants16 : std::false_type {};
+template <class Epi>
+struct wants16<Epi, std::void_t<decltype(Epi::kManyEpilogueWarps)>> : std::true_type {};
+static int epi16_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("FBSNN_EPI16");
+    mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return mode;
+}
+template <class Epi>
+static bool epi16_enabled() {
+  const int mode = epi16_mode();
+  return mode == 2 || (mode == 1 && wants16<Epi>::value);
+}
 static int pair_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -294,7 +316,15 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
       }
     }
     const bool pair = uses_pair<A_KC, B_KC>(s, g, nsplit);
-    if (presplit && pair && g.nseg <= 4) {   // pair sweeps: W_hi / W_lo twins in one stage (SPLIT = 3)
+    bool done16 = false;
+    if constexpr (A_KC && !std::is_same<Epi, EpiPartial>::value) {
+      if (presplit && !pair && epi16_enabled<Epi>() && tc16_eligible<B_KC>(g2, nsplit)) {
+        e = launch_gemm_tc16<B_KC, 1>(g2, epi, num_sms(), st);
+        done16 = true;
+      }
+    }
+    if (done16) {
+    } else if (presplit && pair && g.nseg <= 4) {   // pair sweeps: W_hi / W_lo twins in one stage (SPLIT = 3)
       GemmArgs g3 = g;
       for (int i = 0; i < g.nseg; ++i) {
         const SplitW* w = find_split(g.seg[i].B);
@@ -307,7 +337,14 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
     else e = pair ? launch_gemm_tc2<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st)
                   : launch_gemm_tc<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st);
   } else {
-    e = launch_gemm_tc<A_KC, B_KC, 0>(g, epi, nsplit, num_sms(), st);
+    bool done16 = false;
+    if constexpr (A_KC && !std::is_same<Epi, EpiPartial>::value) {
+      if (epi16_enabled<Epi>() && tc16_eligible<B_KC>(g, nsplit)) {
+        e = launch_gemm_tc16<B_KC, 0>(g, epi, num_sms(), st);
+        done16 = true;
+      }
+    }
+    if (!done16) e = launch_gemm_tc<A_KC, B_KC, 0>(g, epi, nsplit, num_sms(), st);
   }
   if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
   if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "%s gemm %s: %s", tc ? "tcgen05" : "simt", what, cudaGetErrorString(e));

@@ -69,6 +69,7 @@ struct EpiFwdT {
     float4 y;   // h_{l-1} (RES only)
   };
   static constexpr bool kColsum = false;
+  static constexpr bool kManyEpilogueWarps = true;   // instruction-bound epilogue (sine/cosine): 16-warp kernel form
   const float* bias1;
   const float* bias2;  // nullable (NAIS: layer{l}_input.bias)
   const float* res;    // nullable: h_{l-1} (NAIS residual stream)

@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libfbsnn_b200.so")
+LIB_PATH = os.environ.get("FBSNN_LIB_PATH") or os.path.join(_HERE, "libfbsnn_b200.so")   # override: A/B of two builds
 SOURCES = ["fbsnn_api.cu", "mc_pricer.cu"]
 HEADERS = ["common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "gemm_tc16.cuh", "kernels.cuh", "philox.cuh",
            os.path.join("..", "..", "include", "fbsnn_b200.h")]

@@ -360,3 +360,26 @@ def test_fused_path_loss_kernel_matches_row_parallel_kernels(problem):
         assert torch.equal(Ys, Y[lo:lo + 1024])
     assert np.isfinite(loss) and abs(acc_l - loss) <= 5e-6 * abs(loss), (acc_l, loss)
     assert float((acc_g - g).abs().max()) <= 5e-5 * float(g.abs().max())
+
+
+def test_tensor_core_variants_agree_with_fp32_at_large_batch():
+    """M = 16 384 paths (835 584 rows): the large-shape code paths -- persistent multi-tile sweeps, the 16-epilogue-warp
+    F kernel, the CTA-pair weight-gradient kernel with ~11 000-row K chunks, the fused per-path loss kernel -- against
+    the fp32 SIMT variant on the same minibatch and weights."""
+    M = 16384
+    ref = _bsb(M, "fp32")
+    t, W = ref.fetch_minibatch_device(iteration=7)
+    l0, _, Y0, _, g0 = ref.loss_grad_flat(t, W)
+    l0, Y0, g0 = float(l0), Y0.clone(), g0.clone()
+    state = {k: v.clone() for k, v in ref.model.state_dict().items()}
+    del ref
+    torch.cuda.empty_cache()
+    for precision, tol_l, tol_g in (("tf32x3", 2e-5, 2e-4), ("tf32", 1e-2, 8e-2)):
+        sol = _bsb(M, precision)
+        sol.model.load_state_dict(state)
+        l1, _, Y1, _, g1 = sol.loss_grad_flat(t, W)
+        assert abs(float(l1) - l0) <= tol_l * abs(l0), (precision, float(l1), l0)
+        assert float((Y1 - Y0).abs().max()) <= 50 * tol_l * float(Y0.abs().max())
+        assert float((g1 - g0).abs().max()) <= tol_g * float(g0.abs().max()), precision
+        del sol
+        torch.cuda.empty_cache()

@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "gemm_simt.cuh"
@@ -39,6 +41,44 @@ struct TmSet {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Programmatic dependent launch: the dense-layer kernels are launched with programmatic stream serialisation, so
+// their prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel on
+// idle SMs -- what bounds the 37-launch M = 100 step.  pdl_wait() (= cudaGridDependencySynchronize) returns once the
+// previous kernel has completed and flushed; pdl_trigger() lets the NEXT kernel start launching early (it still
+// waits for this one to finish at its own pdl_wait).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FBSNN_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+template <class Kern, class... Args>
+inline cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
 }
@@ -186,6 +226,8 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // everything above overlapped the previous kernel; its outputs are read only from here on
 
   // k-range of one work item (split-K only for the weight-gradient contraction, where K = rows)
   auto kbeg = [&](int s, int split) { return g.kchunk ? (int)min((long long)g.seg[s].K, (long long)split * g.kchunk) : 0; };
@@ -554,8 +596,7 @@ inline cudaError_t launch_gemm_tc_bn(const GemmArgs& g, const Epi& epi, int nspl
   const int mtiles = (g.M + tc::BM - 1) / tc::BM;
   const int work = mtiles * ((g.N + BN - 1) / BN) * nsplit;
   const int grid = work < num_sms ? work : num_sms;
-  kern<<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(tm, g, epi, mtiles, nsplit);
-  return cudaGetLastError();
+  return tc::launch_pdl(kern, grid, C::NUM_THREADS, C::SMEM_BYTES, st, 1, tm, g, epi, mtiles, nsplit);
 }
 
 }  // namespace fbsnn

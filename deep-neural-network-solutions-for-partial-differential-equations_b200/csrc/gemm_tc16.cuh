@@ -82,6 +82,8 @@ gemm_tc16_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi e
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -330,8 +332,7 @@ inline cudaError_t launch_gemm_tc16_bn(const GemmArgs& g, const Epi& epi, int nu
   const int mtiles = (g.M + tc::BM - 1) / tc::BM;
   const int work = mtiles * ((g.N + BN - 1) / BN);
   const int grid = work < num_sms ? work : num_sms;
-  kern<<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(tm, g, epi, mtiles);
-  return cudaGetLastError();
+  return tc::launch_pdl(kern, grid, C::NUM_THREADS, C::SMEM_BYTES, st, 1, tm, g, epi, mtiles);
 }
 
 template <bool B_KC, int SPLIT, class Epi>

@@ -151,6 +151,8 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
   cluster_sync_all();                                   // both CTAs' barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   auto kbeg = [&](int s, int split) { return g.kchunk ? (int)min((long long)g.seg[s].K, (long long)split * g.kchunk) : 0; };
   auto kend = [&](int s, int split) {
@@ -449,17 +451,7 @@ inline cudaError_t launch_gemm_tc2(const GemmArgs& g, const Epi& epi, int nsplit
     attr_set = true;
   }
   const int mtiles2 = (g.M + 255) / 256;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tc2_grid(g, nsplit, num_sms), 1, 1);
-  cfg.blockDim = dim3(C::NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, tm, g, epi, mtiles2, nsplit);
+  return tc::launch_pdl(kern, tc2_grid(g, nsplit, num_sms), C::NUM_THREADS, C::SMEM_BYTES, st, 2, tm, g, epi, mtiles2, nsplit);
 }
 
 }  // namespace fbsnn

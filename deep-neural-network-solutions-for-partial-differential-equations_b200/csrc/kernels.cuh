@@ -6,6 +6,10 @@
 
 namespace fbsnn {
 
+// lets a following dense-layer kernel (launched with programmatic stream serialisation, gemm_tc.cuh) begin its
+// prologue while this kernel is still running; that kernel still waits for this one's completion before reading
+__device__ __forceinline__ void pdl_trigger_next() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Problem constants handed to the path / loss kernels (closed enumeration).
 struct ProblemK {
   int D, N, ldx;
@@ -86,6 +90,7 @@ struct PathArgs {
 };
 
 __global__ void path_advance_kernel(const ProblemK p, const PathArgs a) {
+  pdl_trigger_next();
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= a.M * p.D) return;
   const long long m = idx / p.D;
@@ -132,6 +137,7 @@ __global__ void path_advance_kernel(const ProblemK p, const PathArgs a) {
 // to +-100.  One thread per path; sdw[row] = [(s00+s01) dW, (s10+s11) dW] feeds the generic loss kernels.
 __device__ __forceinline__ float clamp100(float x) { return fminf(fmaxf(x, -100.f), 100.f); }
 __global__ void path_advance_heston_kernel(const ProblemK p, const PathArgs a) {
+  pdl_trigger_next();
   const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (m >= a.M) return;
   const int N = p.N, ldx = p.ldx;
@@ -175,6 +181,7 @@ __global__ void path_advance_heston_kernel(const ProblemK p, const PathArgs a) {
 // mask (nullable) keeps 1{u_raw >= 0} for the seed kernel.
 __global__ void clamp_u_kernel(float* __restrict__ Y, float* __restrict__ zf, int ldx, long long rows,
                                float* __restrict__ mask) {
+  pdl_trigger_next();
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -190,6 +197,7 @@ __global__ void clamp_u_kernel(float* __restrict__ Y, float* __restrict__ zf, in
 
 // rows of arbitrary (t, X) for net_u: xin = [t, X, 0-pad]
 __global__ void pack_rows_kernel(const float* t, const float* X, long long rows, int D, int ldx, float* xin) {
+  pdl_trigger_next();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= rows * ldx) return;
   const long long r = i / ldx;
@@ -199,6 +207,7 @@ __global__ void pack_rows_kernel(const float* t, const float* X, long long rows,
 
 // dst (rows x ldd) = [src (rows x cols) | 0]   (TF32 variant: zero-padded homes of the input-width matrices)
 __global__ void pad_copy_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst, int ldd) {
+  pdl_trigger_next();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ldd) return;
   const int r = i / ldd, c = i % ldd;
@@ -207,6 +216,7 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, int rows, int col
 
 // 3xTF32 variant: hi = x with the 13 low mantissa bits cleared (exactly what the tensor core reads), lo = x - hi
 __global__ void split_hi_lo_kernel(const float* __restrict__ src, int n, float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_trigger_next();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = src[i];
@@ -218,6 +228,7 @@ __global__ void split_hi_lo_kernel(const float* __restrict__ src, int n, float* 
 // u[r] = h_L[r,:] . wout + bout      (one warp per row)
 __global__ void head_kernel(const float* __restrict__ h, int ld, int H, const float* __restrict__ wout,
                             const float* __restrict__ bout, long long rows, float* __restrict__ u) {
+  pdl_trigger_next();
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -338,6 +349,7 @@ __global__ void loss_residual_kernel(const ProblemK p, const LossArgs a) {
 
 // Seeds of the reverse sweeps: ybar = dL/dY, V = [0, dL/dZ, 0-pad] per row.
 __global__ void loss_seed_kernel(const ProblemK p, const LossArgs a) {
+  pdl_trigger_next();
   __shared__ float red[32];
   const int lane = threadIdx.x & 31;
   float ybsum = 0.f;
@@ -401,6 +413,7 @@ __global__ void loss_seed_kernel(const ProblemK p, const LossArgs a) {
 // warp reductions (two rows in flight per warp).  Same arithmetic as the two kernels above.
 // ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) loss_path_kernel(const ProblemK p, const LossArgs a, long long n_paths) {
+  pdl_trigger_next();
   __shared__ float red[32];
   const int lane = threadIdx.x & 31;
   const int N = p.N, D = p.D, ldx = p.ldx;
@@ -514,6 +527,7 @@ struct FinalSum2 {
   float* out1;
 };
 __global__ void final_sum2_kernel(const float* __restrict__ part, int n, FinalSum2 o) {
+  pdl_trigger_next();
   __shared__ double red[32];
   for (int j = 0; j < 2; ++j) {
     float* out = j == 0 ? o.out0 : o.out1;
@@ -611,6 +625,7 @@ __global__ void colsum_stage2_kernel(const ColJobs js) {
 // out[o*ld_out + i] = sum_z part[z][o][i_pad]   (weight-gradient split-K second stage)
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nsplit, int rows, int cols_pad, int cols,
                                        float* __restrict__ out, int ld_out) {
+  pdl_trigger_next();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols_pad) return;
   const int o = idx / cols_pad, i = idx % cols_pad;

@@ -62,6 +62,7 @@ struct Plan {
   bool nais;
   long long rows;
   int loss_blocks, col_blocks, col_rows_per_block, wg_split, wg_chunk, gsq_blocks;
+  size_t wg_stride;   // floats between the per-layer split-K partial buffers (FC)
   // offsets in floats
   size_t xin, sdw, Y, zf, V, ev, ybar, inc, zraw, part_loss, part_wg, part_col, part_gsq, umask;
   size_t g[kMaxL + 2], a[kMaxL + 2], delta[kMaxL + 2], szz[kMaxL + 2], hd[kMaxL + 2], h[kMaxL + 2],
@@ -180,7 +181,8 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
       wg = std::max(wg, (size_t)p.H[l] * (size_t)round_up(p.H[l - 1], 4));
       wg = std::max(wg, (size_t)p.H[l] * (size_t)p.ldx);
     }
-    p.part_wg = take(wg * p.wg_split);
+    p.wg_stride = (wg * p.wg_split + 63) / 64 * 64;
+    p.part_wg = take(p.wg_stride * (p.nais ? 1 : p.L));   // FC: one partial buffer per layer, reduced together
     p.part_col = take((size_t)kMaxColJobs * std::max(p.col_blocks, 256) * 1024);   // 256 >= CTAs of the tcgen05 grid
     p.part_gsq = take(p.gsq_blocks);
     if (p.nais)
@@ -387,9 +389,8 @@ static Net bind_net(const FbsnnSpec* s, const Plan& p, const float* params, floa
 
 // TF32 variant: copy the input-width matrices into their zero-padded (H x ldx) homes
 static int prepare_weights(const FbsnnSpec* s, const Plan& p, const float* params, float* ws, cudaStream_t st) {
-  if (!p.tf32) return 0;
+  if (!p.tf32 || !p.nais) return 0;   // FC: done together with the hi/lo split in split_weights()
   for (int l = 1; l <= p.L; ++l) {
-    if (l >= 2 && !p.nais) break;
     const float* src = params + (l == 1 ? s->off_W[1] : s->off_Win[l]);
     float* dst = ws + (l == 1 ? p.W1p : p.Winp[l]);
     const int n = p.H[l] * p.ldx;
@@ -399,9 +400,27 @@ static int prepare_weights(const FbsnnSpec* s, const Plan& p, const float* param
   return 0;
 }
 
-// 3xTF32: write exact-TF32 hi / lo twins of every weight matrix the sweeps use as their B operand and register them
-static int split_weights(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, cudaStream_t st) {
+// 3xTF32: write exact-TF32 hi / lo twins of every weight matrix the sweeps use as their B operand and register them.
+// FC networks: ONE launch does the zero-padded copy of W_1 and all hi / lo twins (prep_weights_kernel).
+static int split_weights(const FbsnnSpec* s, const Plan& p, const Net& n, const float* params, float* ws, cudaStream_t st) {
   g_nsplitw = 0;
+  if (!p.nais) {
+    if (!p.tf32) return 0;
+    PrepJobs js{};
+    for (int l = 1; l <= p.L; ++l) {
+      if (l >= 2 && !p.x3) break;
+      PrepJob& j = js.job[js.njobs++];
+      const int cols_src = l == 1 ? p.d_in : p.H[l - 1], ld = l == 1 ? p.ldx : p.H[l - 1];
+      j.src = params + s->off_W[l];
+      j.pad = l == 1 ? ws + p.W1p : nullptr;
+      j.hi = p.x3 ? ws + p.Whi[l] : nullptr, j.lo = p.x3 ? ws + p.Wlo[l] : nullptr;
+      j.rows = p.H[l], j.cols = cols_src, j.ld = ld;
+      if (p.x3) g_splitw[g_nsplitw++] = SplitW{n.W[l], ws + p.Whi[l], ws + p.Wlo[l]};
+    }
+    prep_weights_kernel<<<dim3(64, js.njobs), 256, 0, st>>>(js);
+    LAUNCH_CHECK("prep_weights");
+    return 0;
+  }
   if (!p.x3) return 0;
   auto one = [&](const float* src, size_t hi, size_t lo, int count) {
     split_hi_lo_kernel<<<(count + 255) / 256, 256, 0, st>>>(src, count, ws + hi, ws + lo);
@@ -410,7 +429,7 @@ static int split_weights(const FbsnnSpec* s, const Plan& p, const Net& n, float*
   for (int l = 1; l <= p.L; ++l) {
     one(n.W[l], p.Whi[l], p.Wlo[l], p.H[l] * (l == 1 ? p.ldx : p.H[l - 1]));
     LAUNCH_CHECK("split_hi_lo");
-    if (p.nais && l >= 2) {
+    if (l >= 2) {
       one(n.Win[l], p.Winhi[l], p.Winlo[l], p.H[l] * p.ldx);
       LAUNCH_CHECK("split_hi_lo");
     }
@@ -533,16 +552,24 @@ static int run_loss(const FbsnnSpec* s, const Plan& p, float* ws, bool with_grad
   return 0;
 }
 
+// weight-gradient contraction of one layer into split-K partials; `defer` (nullable) collects the second-stage
+// reduction for one batched launch, else it is launched right away
 static int wgrad(const FbsnnSpec* s, const Plan& p, float* ws, const float* P0, const float* Q0, const float* P1,
-                 const float* Q1, int out, int in_pad, int in_valid, int ldq, float* dst, int ld_dst, cudaStream_t st) {
+                 const float* Q1, int out, int in_pad, int in_valid, int ldq, float* dst, int ld_dst, cudaStream_t st,
+                 RedJobs* defer = nullptr, size_t part_off = 0) {
   GemmArgs g{};
   g.M = out, g.N = in_pad, g.Nb = in_pad, g.kchunk = p.wg_chunk, g.nseg = 2;
   g.seg[0] = GemmSeg{P0, Q0, out, ldq, (int)p.rows};
   g.seg[1] = GemmSeg{P1, Q1, out, ldq, (int)p.rows};
-  int rc = dense<false, false>(s, g, EpiPartial{ws + p.part_wg, out, in_pad}, p.wg_split, st, "G");
+  float* part = ws + p.part_wg + part_off;
+  int rc = dense<false, false>(s, g, EpiPartial{part, out, in_pad}, p.wg_split, st, "G");
   if (rc) return rc;
+  if (defer) {
+    defer->job[defer->njobs++] = RedJob{part, dst, out, in_pad, in_valid, ld_dst};
+    return 0;
+  }
   const int n = out * in_pad;
-  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws + p.part_wg, p.wg_split, out, in_pad, in_valid, dst, ld_dst);
+  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, p.wg_split, out, in_pad, in_valid, dst, ld_dst);
   LAUNCH_CHECK("reduce_partials");
   return 0;
 }
@@ -599,17 +626,22 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     if (rc) return rc;
   }
   // ---- G contractions ------------------------------------------------------------------------------------
+  RedJobs red{};
+  red.nsplit = p.wg_split;
+  RedJobs* defer = p.nais ? nullptr : &red;   // FC: the L contractions run back to back, one reduction launch after
+  const size_t wg_stride = p.wg_stride;
   for (int l = 1; l <= p.L; ++l) {
     int rc;
+    const size_t poff = defer ? (size_t)(l - 1) * wg_stride : 0;
     if (l == 1) {
       rc = wgrad(s, p, ws, ws + p.szz[1], ws + p.xin, ws + p.delta[1], ws + p.V, p.H[1], p.ldx, p.d_in, p.ldx,
-                 grads + s->off_W[1], p.d_in, st);
+                 grads + s->off_W[1], p.d_in, st, defer, poff);
       if (rc) return rc;
       continue;
     }
     float* dst = p.nais ? ws + p.Bbar[l] : grads + s->off_W[l];
     rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.h[l - 1], ws + p.delta[l], ws + p.hd[l - 1], p.H[l], p.H[l - 1],
-               p.H[l - 1], p.H[l - 1], dst, p.H[l - 1], st);
+               p.H[l - 1], p.H[l - 1], dst, p.H[l - 1], st, defer, poff);
     if (rc) return rc;
     if (p.nais) {
       rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.xin, ws + p.delta[l], ws + p.V, p.H[l], p.ldx, p.d_in, p.ldx,
@@ -624,6 +656,12 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
       rc = dense<true, false>(s, g, EpiStore{grads + s->off_W[l], H}, 1, st, "nais Wbar", false);
       if (rc) return rc;
     }
+  }
+  if (defer && red.njobs > 0) {
+    int maxn = 0;
+    for (int i = 0; i < red.njobs; ++i) maxn = std::max(maxn, red.job[i].rows * red.job[i].cols_pad);
+    reduce_partials_batched_kernel<<<dim3((maxn + 255) / 256, red.njobs), 256, 0, st>>>(red);
+    LAUNCH_CHECK("reduce_partials_batched");
   }
   // ---- bias / output-layer gradients: column sums -----------------------------------------------------------
   ColJobs js{};
@@ -703,7 +741,7 @@ static int loss_grad_impl(const FbsnnSpec* s, const float* params, float* grads,
   const Net n = bind_net(s, p, params, ws);
   if ((rc = prepare_weights(s, p, params, ws, st))) return rc;
   if (p.nais && (rc = nais_prepare(s, p, n, ws, st))) return rc;
-  if ((rc = split_weights(s, p, n, ws, st))) return rc;
+  if ((rc = split_weights(s, p, n, params, ws, st))) return rc;
   if (!W && (rc = gen_increments(s, p, ws, M, T, path_offset, seed, iteration, iter_dev, chol, st))) return rc;
   {
     const ProblemK k = problem_k(s, p);
@@ -877,7 +915,7 @@ int fbsnn_net_u(const FbsnnSpec* spec, const float* params, const float* t, cons
   const Net n = bind_net(spec, p, params, ws);
   if ((rc = prepare_weights(spec, p, params, ws, st))) return rc;
   if (p.nais && (rc = nais_prepare(spec, p, n, ws, st))) return rc;
-  if ((rc = split_weights(spec, p, n, ws, st))) return rc;
+  if ((rc = split_weights(spec, p, n, params, ws, st))) return rc;
   const long long tot = rows * p.ldx;
   pack_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(t, X, rows, spec->D, p.ldx, ws + p.xin);
   LAUNCH_CHECK("pack_rows");

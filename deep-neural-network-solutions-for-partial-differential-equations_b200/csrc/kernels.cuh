@@ -105,10 +105,8 @@ __global__ void path_advance_kernel(const ProblemK p, const PathArgs a) {
     const long long r = row0 + n;
     float* xr = a.xin + r * ldx;
     xr[1 + d] = x;
-    if (d == 0) {
-      xr[0] = tn;
-      for (int c = D + 1; c < ldx; ++c) xr[c] = 0.f;
-    }
+    if (d == 0) xr[0] = tn;
+    for (int c = D + 1 + d; c < ldx; c += D) xr[c] = 0.f;   // zero padding, spread over the path's D threads
     if (a.X_out) a.X_out[r * D + d] = x;
     if (n == N) break;
     const float tn1 = a.t ? __ldg(a.t + r + 1) : (float)((double)(n + 1) * (double)a.T / (double)N);
@@ -633,6 +631,58 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int nspli
   float acc = 0.f;
   for (int z = 0; z < nsplit; ++z) acc += part[(size_t)z * rows * cols_pad + idx];
   out[(size_t)o * ld_out + i] = acc;
+}
+
+// the same for up to kMaxRedJobs layers in one launch (blockIdx.y = job): the FC network's weight-gradient
+// contractions run back to back into per-layer partial buffers and are reduced together
+constexpr int kMaxRedJobs = 10;
+struct RedJob {
+  const float* part;
+  float* out;
+  int rows, cols_pad, cols, ld_out;
+};
+struct RedJobs {
+  RedJob job[kMaxRedJobs];
+  int njobs, nsplit;
+};
+__global__ void reduce_partials_batched_kernel(const RedJobs js) {
+  const RedJob& j = js.job[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= j.rows * j.cols_pad) return;
+  const int o = idx / j.cols_pad, i = idx % j.cols_pad;
+  if (i >= j.cols) return;
+  float acc = 0.f;
+  for (int z = 0; z < js.nsplit; ++z) acc += j.part[(size_t)z * j.rows * j.cols_pad + idx];
+  j.out[(size_t)o * j.ld_out + i] = acc;
+}
+
+// One launch for the per-iteration weight preparation of the tensor-core variants: job = (src rows x cols) ->
+// zero-padded copy (rows x ld) [TF32 input-width matrices] and / or its exact-TF32 hi / lo twins [3xTF32]
+constexpr int kMaxPrepJobs = 20;
+struct PrepJob {
+  const float* src;
+  float* pad;   // nullable
+  float* hi;    // nullable (with lo)
+  float* lo;
+  int rows, cols, ld;
+};
+struct PrepJobs {
+  PrepJob job[kMaxPrepJobs];
+  int njobs;
+};
+__global__ void prep_weights_kernel(const PrepJobs js) {
+  pdl_trigger_next();
+  const PrepJob& j = js.job[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.rows * j.ld; i += gridDim.x * blockDim.x) {
+    const int r = i / j.ld, c = i % j.ld;
+    const float x = c < j.cols ? j.src[(size_t)r * j.cols + c] : 0.f;
+    if (j.pad) j.pad[i] = x;
+    if (j.hi) {
+      const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+      j.hi[i] = h;
+      j.lo[i] = x - h;
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -323,11 +323,13 @@ inline cudaError_t launch_gemm_tc16_bn(const GemmArgs& g, const Epi& epi, int nu
   }
   for (int s = g.nseg; s < kMaxSeg; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];
   auto kern = tc16::gemm_tc16_kernel<B_MN, SPLIT, BN, Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;   // per device: opt in to the large dynamic shared memory once
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
+  if (!((attr_devs >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_devs |= 1ull << dev;
   }
   const int mtiles = (g.M + tc::BM - 1) / tc::BM;
   const int work = mtiles * ((g.N + BN - 1) / BN);

@@ -444,11 +444,13 @@ inline cudaError_t launch_gemm_tc2(const GemmArgs& g, const Epi& epi, int nsplit
     }
   }
   auto kern = tc2::gemm_tc2_kernel<A_MN, B_MN, SPLIT, Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;   // per device: opt in to the large dynamic shared memory once
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
+  if (!((attr_devs >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_devs |= 1ull << dev;
   }
   const int mtiles2 = (g.M + 255) / 256;
   return tc::launch_pdl(kern, tc2_grid(g, nsplit, num_sms), C::NUM_THREADS, C::SMEM_BYTES, st, 2, tm, g, epi, mtiles2, nsplit);

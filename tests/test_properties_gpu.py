@@ -383,3 +383,29 @@ def test_tensor_core_variants_agree_with_fp32_at_large_batch():
         assert float((g1 - g0).abs().max()) <= tol_g * float(g0.abs().max()), precision
         del sol
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("mode", ["FC", "Naisnet"])
+@pytest.mark.parametrize("H", [64, 128, 192, 256])
+@pytest.mark.parametrize("M", [3, 200, 1500])
+def test_tensor_core_kernel_forms_across_shapes(mode, H, M):
+    """Every dispatch of the tcgen05 kernels (8- and 16-epilogue-warp sweeps, CTA-pair weight gradients, narrow
+    column tiles at few row tiles, fused bias column sums indexed per CTA or per m-tile, SIMT for what does not fit)
+    against the fp32 SIMT variant: hidden widths 64..256, FC and NAIS-Net, ragged row counts."""
+    import dnnpde_b200 as pde
+    Dd, Nn = 31, 7                                     # d_in = 32: the input-width GEMMs are tensor-core eligible too
+    layers = [Dd + 1, H, H, H, 1]
+    torch.manual_seed(H + M)
+    args = (np.ones((1, Dd)), 1.0, M, Nn, Dd, None, layers, mode, "Sine")
+    ref = pde.BasketCallOption(*args, precision="fp32", seed=3)
+    t, W = ref.fetch_minibatch_device(iteration=1)
+    l0, _, Y0, Z0, g0 = ref.loss_grad_flat(t, W, want_Z=True)
+    l0, Y0, Z0, g0 = float(l0), Y0.clone(), Z0.clone(), g0.clone()
+    for precision, tl, tg in (("tf32x3", 5e-5, 5e-4), ("tf32", 2e-2, 1e-1)):
+        sol = pde.BasketCallOption(*args, precision=precision, seed=3)
+        sol.model.load_state_dict(ref.model.state_dict())
+        l1, _, Y1, Z1, g1 = sol.loss_grad_flat(t, W, want_Z=True)
+        assert abs(float(l1) - l0) <= tl * abs(l0) + 1e-7, (precision, float(l1), l0)
+        assert float((Y1 - Y0).abs().max()) <= 20 * tl * float(Y0.abs().max()) + 1e-6
+        assert float((Z1 - Z0).norm()) <= 20 * tl * float(Z0.norm()) + 1e-6
+        assert float((g1 - g0).abs().max()) <= tg * float(g0.abs().max()) + 1e-7, precision

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("FBSNN_LIB_PATH") or os.path.join(_HERE, "libfbsnn_b200.so")   # override: A/B of two builds
 SOURCES = ["fbsnn_api.cu", "mc_pricer.cu"]
-HEADERS = ["common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "gemm_tc16.cuh", "kernels.cuh", "philox.cuh",
+HEADERS = ["common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "gemm_tc16.cuh", "gemm_tc2g.cuh", "kernels.cuh", "philox.cuh",
            os.path.join("..", "..", "include", "fbsnn_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

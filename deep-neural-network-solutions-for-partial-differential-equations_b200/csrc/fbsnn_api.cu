@@ -13,6 +13,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc16.cuh"
+#include "gemm_tc2g.cuh"
 #include "kernels.cuh"
 
 namespace fbsnn {
@@ -261,6 +262,15 @@ static bool epi16_enabled() {
   const int mode = epi16_mode();
   return mode == 2 || (mode == 1 && wants16<Epi>::value);
 }
+// weight gradients on the pair with the A operand in tensor memory (gemm_tc2g.cuh); FBSNN_GTMEM=0: A in shared memory
+static bool gtmem_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FBSNN_GTMEM");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 static int pair_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -336,8 +346,17 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
       e = launch_gemm_tc2<A_KC, B_KC, 3>(g3, epi, nsplit, num_sms(), st);
     } else if (presplit) e = pair ? launch_gemm_tc2<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st)
                            : launch_gemm_tc<A_KC, B_KC, 1>(g2, epi, nsplit, num_sms(), st);
-    else e = pair ? launch_gemm_tc2<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st)
-                  : launch_gemm_tc<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st);
+    else {
+      bool doneg = false;
+      if constexpr (!A_KC && !B_KC && std::is_same<Epi, EpiPartial>::value) {
+        if (pair && gtmem_enabled() && tc2g_eligible(g, nsplit)) {
+          e = launch_gemm_tc2g(g, epi, nsplit, num_sms(), st);
+          doneg = true;
+        }
+      }
+      if (!doneg) e = pair ? launch_gemm_tc2<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st)
+                           : launch_gemm_tc<A_KC, B_KC, 2>(g, epi, nsplit, num_sms(), st);
+    }
   } else {
     bool done16 = false;
     if constexpr (A_KC && !std::is_same<Epi, EpiPartial>::value) {
@@ -835,7 +854,23 @@ int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const 
   if (use_tc) {
     bool ok = a_kc && b_kc ? tc_eligible<true, true>(g, 1) : (a_kc ? tc_eligible<true, false>(g, 1) : tc_eligible<false, false>(g, 1));
     if (!ok || (!a_kc && b_kc)) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the tcgen05 kernel");
-    if (use_tc == 4) {   // CTA-pair kernel, B pre-split into exact-TF32 hi / lo twins (the sweeps' form); test hook only
+    if (use_tc == 5) {   // CTA-pair weight-gradient kernel with A in tensor memory: split-K over K, partials summed here
+      if (a_kc || b_kc) return fail(FBSNN_E_UNSUPPORTED, "the TMEM-A kernel takes the weight-gradient layout only");
+      GemmArgs gg = g;
+      const int nsp = std::max(1, std::min(8, K / 64));
+      gg.kchunk = ((K + nsp - 1) / nsp + 31) / 32 * 32;
+      const int nsplit = (K + gg.kchunk - 1) / gg.kchunk;
+      if (!tc2g_eligible(gg, nsplit)) return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the TMEM-A kernel");
+      float* part = nullptr;
+      if (cudaMalloc(&part, (size_t)nsplit * M * N * sizeof(float)) != cudaSuccess) return fail(FBSNN_E_CUDA, "cudaMalloc");
+      err = launch_gemm_tc2g(gg, EpiPartial{part, M, N}, nsplit, num_sms(), st);
+      if (err == cudaSuccess) {
+        reduce_partials_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(part, nsplit, M, N, N, C, ldc);
+        err = cudaGetLastError();
+      }
+      cudaStreamSynchronize(st);
+      cudaFree(part);
+    } else if (use_tc == 4) {   // CTA-pair kernel, B pre-split into exact-TF32 hi / lo twins (the sweeps' form); test hook only
       if (!a_kc) return fail(FBSNN_E_UNSUPPORTED, "pre-split B is the sweeps' form (A k-contiguous)");
       if (!(b_kc ? tc2_eligible<true, true>(g, 1) : tc2_eligible<true, false>(g, 1)))
         return fail(FBSNN_E_UNSUPPORTED, "shape not eligible for the CTA-pair tcgen05 kernel");

@@ -87,3 +87,17 @@ def test_tcgen05_cta_pair_presplit_weights(b_kc, M, N, K):
     assert torch.isfinite(C).all()
     err = (C.double() - ref).abs()
     assert (err <= 2e-6 * bound + 1e-6).all(), float((err / (bound + 1e-9)).max())
+
+
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 1000), (128, 4100), (64, 300), (192, 20000), (256, 200003)])
+def test_tcgen05_cta_pair_tmem_a_weight_gradient(N, K):
+    """weight-gradient kernel with the A operand in tensor memory (tcgen05.st by four warps, tcgen05.mma with A from
+    TMEM): out = 256, K = rows incl. counts that are not multiples of 32, split-K partials reduced by the hook."""
+    C, ref, bound = run_gemm(0, 0, 5, 256, N, K)
+    assert torch.isfinite(C).all()
+    err = (C.double() - ref).abs()
+    tol = 2e-6 if K <= 50000 else 5e-6          # fp32 accumulation over 25 000-row chunks: ~2^-24 sqrt(K) on top
+    assert (err <= tol * bound + 1e-6).all(), float((err / (bound + 1e-9)).max())
+    if K > 50000:                              # same accumulation length on the shared-memory-A pair kernel: same error level
+        C3, _, _ = run_gemm(0, 0, 3, 256, N, K)
+        assert float((C3.double() - ref).abs().max()) >= 0.2 * float(err.max())

@@ -139,8 +139,8 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b[s]) : "memory");
     }
     for (int i = 0; i < STAGES; ++i)
-      mbar_init(&full[i], 1), mbar_init(&empty[i], 1), mbar_init(&sdone[i], 2 * C::SPLIT_TEAM_WARPS);
-    for (int i = 0; i < 2; ++i) mbar_init(&tfull[i], 1), mbar_init(&tempty[i], 2 * NUM_EPI_WARPS);
+      mbar_init(&full[i], 1), mbar_init(&empty[i], 1), mbar_init(&sdone[i], 2);   // one arrival per CTA (see below)
+    for (int i = 0; i < 2; ++i) mbar_init(&tfull[i], 1), mbar_init(&tempty[i], 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -306,9 +306,11 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
             if (ch == k) csum[k].x += cs.x, csum[k].y += cs.y, csum[k].z += cs.z, csum[k].w += cs.w;
         }
       }
+      // the eight epilogue warps meet on a named barrier and ONE thread signals the leader: a cluster-scope release
+      // arrive is a gpu-wide fence (30 % of the stall samples of the weight-gradient kernel when every warp did it)
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cta(&tempty[acc], 0);
+      asm volatile("bar.sync 3, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+      if (threadIdx.x == 32 * C::EPI_WARP0) mbar_arrive_cta(&tempty[acc], 0);
     };
 
     constexpr int TEAM = 32 * C::SPLIT_TEAM_WARPS;
@@ -342,8 +344,8 @@ gemm_tc2_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi ep
               }
           }
           asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores -> UMMA (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cta(&sdone[sstage], 0);
+          asm volatile("bar.sync 2, %0;" ::"n"(TEAM) : "memory");
+          if (threadIdx.x == 64) mbar_arrive_cta(&sdone[sstage], 0);
           if (++sstage == STAGES) sstage = 0, sphase ^= 1;
         }
       }

@@ -92,6 +92,31 @@ def test_same_seed_gives_reference_initial_weights_on_cpu():
             assert k1 == k2 and torch.equal(v1, v2)
 
 
+@pytest.mark.parametrize("name", ["heston_fc_sine", "heston_nais_tanh_smooth"])
+def test_heston_constructor_reproduces_reference_initial_weights(name):
+    """HestonFBSNN builds its network like heston_dnnpde.py:519-585 (base net with layers[0] inputs, input layer(s)
+    swapped for 3 inputs, xavier gain 0.5, zero biases): the same torch seed gives the REFERENCE's initial weights
+    (parameter checksums stored in the fixture), and the same NumPy seed its first Brownian minibatch."""
+    g, meta = gu.load(name)
+    torch.manual_seed(meta["torch_seed"])
+    np.random.seed(meta["numpy_seed"])
+    sol = pde.HestonFBSNN(gu.make_xi("ones", 1), meta["T"], meta["M"], meta["N"], 1, int(meta["N"] ** (1 / 5)),
+                          meta["layers"], meta["mode"], meta["act"], payoff_type=meta["payoff"], device="cpu")
+    names = [k for k, _ in sol.model.named_parameters()]
+    assert names == [str(x) for x in g["param_names"]]
+    sums = np.array([float(p.detach().double().sum()) for _, p in sol.model.named_parameters()])
+    asums = np.array([float(p.detach().double().abs().sum()) for _, p in sol.model.named_parameters()])
+    assert np.allclose(sums, g["param_sum"], rtol=0, atol=1e-12) and np.allclose(asums, g["param_abssum"], rtol=0, atol=1e-12)
+    t, W = sol.fetch_minibatch()
+    assert W.shape == (meta["M"], meta["N"] + 1, 1)
+    wsum = np.array([float(W.double().sum()), float(W.double().abs().sum())])
+    assert np.allclose(wsum, g["W_sum"], rtol=1e-12)
+    sp = sol._spec()
+    assert (sp.D, sp.noise_dim, sp.clamp_u, sp.zt_dims) == (2, 1, 1, 1) and sol.D == 1 and sol._fp.is_intact()
+    with pytest.raises(RuntimeError):
+        sol.net_u(np.zeros((2, 1)), np.ones((2, 2)))          # no CPU fallback
+
+
 def test_fetch_minibatch_is_the_reference_numpy_stream():
     g, meta = gu.load("basket10_nais_sine_5l")
     oracle = gu.rebuild_inputs(meta, g)
@@ -143,6 +168,25 @@ def test_compute_fails_loudly_without_cuda():
     model = pde.BlackScholesModel(0.05, 0.2, 5, True)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pde.MonteCarloPricer(model, pde.BasketOption(np.ones(5) / 5, 1.0), 1.0, 50, 1000).price(np.ones(5))
+    pr = pde.MonteCarloPricer(model, pde.BasketOption(np.ones(5) / 5, 1.0), 1.0, 50, 1000)
+    for call in (lambda: pr.price_and_delta(np.ones(5)), lambda: pde.hjb_u_exact(np.zeros((3, 1)), np.ones((3, 4))),
+                 lambda: pde.basket_pricer.MonteCarloSimulator(np.ones(3), 0.05, 0.2, 1.0, 0.1).simulate(10)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
+def test_basket_pricer_host_surface():
+    """basket_pricer.py:7-39 host-side pieces: step count, Cholesky factor, positive-definite repair."""
+    bp = pde.basket_pricer
+    sim = bp.MonteCarloSimulator(np.ones(3), 0.05, 0.2, 1.0, 0.25, np.eye(3))
+    assert sim.num_assets == 3 and sim.num_steps == 4 and np.allclose(sim.L, np.eye(3))
+    bad = np.array([[1.0, 1.0], [1.0, 1.0]])                       # singular: repaired by adding eps * I
+    fixed = bp.MonteCarloSimulator(np.ones(2), 0.05, 0.2, 1.0, 0.5, bad)
+    assert np.all(np.linalg.eigvalsh(fixed.correlation_matrix) > 0) and np.array_equal(bad, [[1.0, 1.0], [1.0, 1.0]])
+    assert bp.MonteCarloSimulator(np.ones(2), 0.05, 0.2, 1.0, 0.5).correlation_matrix is None
+    paths = np.ones((2, 3, 5))
+    paths[:, -1, :] = [[1.5] * 5, [0.9] * 5]
+    assert abs(bp.BasketOptionPricer(1.0, 1.0).price(paths, 0.05) - np.exp(-0.05) * 0.2) < 1e-12
 
 
 def test_mc_host_objects_match_reference():

@@ -258,9 +258,15 @@ static int epi16_mode() {
   return mode;
 }
 template <class Epi>
-static bool epi16_enabled() {
+static bool epi16_enabled(const Epi& epi, bool x3) {
   const int mode = epi16_mode();
-  return mode == 2 || (mode == 1 && wants16<Epi>::value);
+  if (mode == 2) return true;
+  if constexpr (wants16<Epi>::value) {
+    // the last hidden layer's F epilogue also writes delta_L and s_L (four row arrays): store-bound; same box, 16- vs
+    // 8-warp form: 4.44 vs 4.58 ms (3xTF32, keep 16), 4.4 vs 3.5 ms (TF32, use 8)
+    return mode == 1 && (x3 || epi.wout == nullptr);
+  }
+  return false;
 }
 // weight gradients on the pair with the A operand in tensor memory (gemm_tc2g.cuh); FBSNN_GTMEM=0: A in shared memory
 static bool gtmem_enabled() {
@@ -330,7 +336,7 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
     const bool pair = uses_pair<A_KC, B_KC>(s, g, nsplit);
     bool done16 = false;
     if constexpr (A_KC && !std::is_same<Epi, EpiPartial>::value) {
-      if (presplit && !pair && epi16_enabled<Epi>() && tc16_eligible<B_KC>(g2, nsplit)) {
+      if (presplit && !pair && epi16_enabled(epi, true) && tc16_eligible<B_KC>(g2, nsplit)) {
         e = launch_gemm_tc16<B_KC, 1>(g2, epi, num_sms(), st);
         done16 = true;
       }
@@ -360,7 +366,7 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
   } else {
     bool done16 = false;
     if constexpr (A_KC && !std::is_same<Epi, EpiPartial>::value) {
-      if (epi16_enabled<Epi>() && tc16_eligible<B_KC>(g, nsplit)) {
+      if (epi16_enabled(epi, false) && tc16_eligible<B_KC>(g, nsplit)) {
         e = launch_gemm_tc16<B_KC, 0>(g, epi, num_sms(), st);
         done16 = true;
       }

@@ -277,6 +277,14 @@ static bool gtmem_enabled() {
   }
   return on == 1;
 }
+static bool narrow3_enabled() {   // FBSNN_NARROW3=0: Du through the two-segment (SPLIT = 1) form
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FBSNN_NARROW3");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 static int pair_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -341,7 +349,21 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
         done16 = true;
       }
     }
-    if (done16) {
+    bool done3 = false;
+    if constexpr (A_KC && !std::is_same<Epi, EpiPartial>::value) {
+      // narrow sweeps (Du: 128 columns): hi / lo weight twins in one 64 KB stage, the A tile fetched once
+      if (!done16 && presplit && !pair && g.N <= 128 && g.nseg <= 4 && narrow3_enabled()) {
+        GemmArgs g3 = g;
+        for (int i = 0; i < g.nseg; ++i) {
+          const SplitW* w = find_split(g.seg[i].B);
+          g3.seg[i].B = w->hi;
+          g3.seg[i + 4] = g.seg[i], g3.seg[i + 4].B = w->lo;
+        }
+        e = launch_gemm_tc<A_KC, B_KC, 3>(g3, epi, nsplit, num_sms(), st);
+        done3 = true;
+      }
+    }
+    if (done16 || done3) {
     } else if (presplit && pair && g.nseg <= 4) {   // pair sweeps: W_hi / W_lo twins in one stage (SPLIT = 3)
       GemmArgs g3 = g;
       for (int i = 0; i < g.nseg; ++i) {

@@ -171,7 +171,9 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b
 template <int SPLIT, int BN = 256>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGES = (SPLIT == 2 && BN == 256) ? 2 : 3;
+  // SPLIT == 3 (sweeps no wider than 128 columns, e.g. Du): W_hi / W_lo twins (seg[s].B / seg[s + 4].B) land in the
+  // B / B_lo slots of ONE stage, only A is split in-kernel and the A tile is fetched once instead of twice
+  static constexpr int STAGES = (SPLIT >= 2 && BN == 256) ? 2 : 3;
   static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
   static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
   // SPLIT == 2 (weight gradients): the epilogue warps are idle during the long K loop of a work item, so they
@@ -179,7 +181,7 @@ struct Cfg {
   static constexpr int SPLIT_TEAM_WARPS = SPLIT == 2 ? SPLIT_WARPS + 8 : SPLIT_WARPS;
   static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES + (SPLIT >= 1 ? A_STAGE_BYTES : 0) +
-                                     (SPLIT == 2 ? B_BYTES : 0);   // [A][B]([A_lo]([B_lo]))
+                                     (SPLIT >= 2 ? B_BYTES : 0);   // [A][B]([A_lo]([B_lo]))
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES + 1024 /*align*/ + 256;
 };
 
@@ -239,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t bytes = A_STAGE_BYTES + (uint32_t)N * BK * 4;
+      const uint32_t bytes = A_STAGE_BYTES + (uint32_t)N * BK * 4 * (SPLIT == 3 ? 2 : 1);
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int mt = w % num_mtiles, nt = (w % num_mn) / num_mtiles, split = w / num_mn;
         const int m0 = mt * BM, n0 = nt * BN;
@@ -259,6 +261,14 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
               for (int c = 0; c < N / 32; ++c) tma_load_2d(b + c * 4096, &tm.b[s], &full[stage], n0 + 32 * c, k0);
             } else {
               tma_load_2d(b, &tm.b[s], &full[stage], k0, n0);
+            }
+            if (SPLIT == 3) {   // W_lo twin -> the B_lo slot
+              uint8_t* bl = b + B_STAGE_BYTES + A_STAGE_BYTES;
+              if (B_MN) {
+                for (int c = 0; c < N / 32; ++c) tma_load_2d(bl + c * 4096, &tm.b[s + 4], &full[stage], n0 + 32 * c, k0);
+              } else {
+                tma_load_2d(bl, &tm.b[s + 4], &full[stage], k0, n0);
+              }
             }
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
@@ -284,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
             const uint32_t a = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t b = a + A_STAGE_BYTES;
             const uint32_t alo = a + A_STAGE_BYTES + B_STAGE_BYTES, blo = alo + A_STAGE_BYTES;
-            const int mode = SPLIT == 2 ? 3 : (SPLIT == 1 ? g.mode[s] : 0);
+            const int mode = SPLIT >= 2 ? 3 : (SPLIT == 1 ? g.mode[s] : 0);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               auto da = [&](uint32_t base) { return A_MN ? make_desc(base + k * 1024, 4096, 512, 1) : make_desc(base + k * 32, 16, 1024, 2); };
@@ -293,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
                 umma_tf32(tmem_d, da(alo), db(b), idesc, first ? 0u : 1u);
                 first = 0;
               }
-              if (SPLIT == 2) umma_tf32(tmem_d, da(a), db(blo), idesc, 1u);
+              if (SPLIT >= 2) umma_tf32(tmem_d, da(a), db(blo), idesc, 1u);
               umma_tf32(tmem_d, da(a), db(b), idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -410,7 +420,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
           float4* lo = (float4*)(smem + sstage * C::STAGE_BYTES + A_STAGE_BYTES + B_STAGE_BYTES);
           // A and B tiles are contiguous ([A 16K][B N*128]) and so are their lo twins: one flat loop, 8 loads in
           // flight per thread.  SPLIT == 1: only A (mode 1 segments), nothing for the W_lo segments (mode 2).
-          const int n4 = SPLIT == 2 ? nA4 + nB4 : (g.mode[s] == 1 ? nA4 : 0);
+          const int n4 = SPLIT == 2 ? nA4 + nB4 : (SPLIT == 3 || g.mode[s] == 1 ? nA4 : 0);
           for (int i0 = ts; i0 < n4; i0 += TEAM * 8) {
             float4 x[8];
 #pragma unroll
@@ -442,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi
         split_item(w);
         if (is_epi) drain(w, it);
       }
-    } else if (SPLIT == 1 && !is_epi) {
+    } else if ((SPLIT == 1 || SPLIT == 3) && !is_epi) {
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) split_item(w);
     } else {
       uint32_t it = 0;
@@ -543,7 +553,7 @@ inline bool tc_eligible(const GemmArgs& g, int nsplit) {
 // most SMs idle -- the narrowest of 128 / 64 that still gives every CTA at most one work item
 template <bool A_KC, int SPLIT>
 inline int tc_pick_bn(const GemmArgs& g, int nsplit, int num_sms) {
-  if (!A_KC || SPLIT == 2 || nsplit != 1 || g.N % 128) return 256;
+  if (!A_KC || SPLIT >= 2 || nsplit != 1 || g.N % 128) return 256;
   const int mtiles = (g.M + tc::BM - 1) / tc::BM;
   if (g.N == 256 && mtiles * 4 <= num_sms) return 64;
   if (mtiles * (g.N / 128) <= num_sms && g.N > 128) return 128;
@@ -563,6 +573,7 @@ inline cudaError_t launch_gemm_tc_bn(const GemmArgs& g, const Epi& epi, int nspl
 
 template <bool A_KC, bool B_KC, int SPLIT, class Epi>
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
+  if constexpr (SPLIT == 3) return launch_gemm_tc_bn<A_KC, B_KC, 3, Epi, 128>(g, epi, nsplit, num_sms, st);   // N <= 128 only
   if constexpr (A_KC && SPLIT != 2) {
     const int bn = tc_pick_bn<A_KC, SPLIT>(g, nsplit, num_sms);
     if (bn == 64) return launch_gemm_tc_bn<A_KC, B_KC, SPLIT, Epi, 64>(g, epi, nsplit, num_sms, st);
@@ -586,6 +597,16 @@ inline cudaError_t launch_gemm_tc_bn(const GemmArgs& g, const Epi& epi, int nspl
     if (!ok) return cudaErrorInvalidValue;
   }
   for (int s = g.nseg; s < kMaxSeg; ++s) tm.a[s] = tm.a[0], tm.b[s] = tm.b[0];
+  if (SPLIT == 3) {   // lo twins of the weight operands ride in seg[s + 4].B
+    if (g.nseg > 4) return cudaErrorInvalidValue;
+    for (int s = 0; s < g.nseg; ++s) {
+      const GemmSeg& sg = g.seg[s];
+      const float* lo = g.seg[s + 4].B;
+      const bool ok = B_MN ? tc::make_map(&tm.b[s + 4], lo, g.Nb, sg.K, sg.ldb, 32, 32, true)
+                           : tc::make_map(&tm.b[s + 4], lo, sg.K, g.Nb, sg.ldb, 32, g.N < BN ? g.N : BN, false);
+      if (!ok || !lo) return cudaErrorInvalidValue;
+    }
+  }
   auto kern = tc::gemm_tc_kernel<A_MN, B_MN, SPLIT, BN, Epi>;
   static unsigned long long attr_devs = 0;   // per device: opt in to the large dynamic shared memory once
   int dev = 0;

@@ -277,13 +277,13 @@ static bool gtmem_enabled() {
   }
   return on == 1;
 }
-static bool narrow3_enabled() {   // FBSNN_NARROW3=0: Du through the two-segment (SPLIT = 1) form
-  static int on = -1;
-  if (on < 0) {
+static int narrow3_mode() {   // FBSNN_NARROW3=0: Du through the two-segment (SPLIT = 1) form; =2: every 8-warp sweep on SPLIT = 3
+  static int mode = -1;
+  if (mode < 0) {
     const char* e = getenv("FBSNN_NARROW3");
-    on = (e && e[0] == '0') ? 0 : 1;
+    mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
-  return on == 1;
+  return mode;
 }
 static int pair_mode() {
   static int mode = -1;
@@ -352,7 +352,7 @@ static int dense(const FbsnnSpec* s, const GemmArgs& g, const Epi& epi, int nspl
     bool done3 = false;
     if constexpr (A_KC && !std::is_same<Epi, EpiPartial>::value) {
       // narrow sweeps (Du: 128 columns): hi / lo weight twins in one 64 KB stage, the A tile fetched once
-      if (!done16 && presplit && !pair && g.N <= 128 && g.nseg <= 4 && narrow3_enabled()) {
+      if (!done16 && presplit && !pair && g.nseg <= 4 && (narrow3_mode() == 2 || (narrow3_mode() == 1 && g.N <= 128))) {
         GemmArgs g3 = g;
         for (int i = 0; i < g.nseg; ++i) {
           const SplitW* w = find_split(g.seg[i].B);

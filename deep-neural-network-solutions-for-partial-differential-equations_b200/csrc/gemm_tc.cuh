@@ -573,7 +573,10 @@ inline cudaError_t launch_gemm_tc_bn(const GemmArgs& g, const Epi& epi, int nspl
 
 template <bool A_KC, bool B_KC, int SPLIT, class Epi>
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const Epi& epi, int nsplit, int num_sms, cudaStream_t st) {
-  if constexpr (SPLIT == 3) return launch_gemm_tc_bn<A_KC, B_KC, 3, Epi, 128>(g, epi, nsplit, num_sms, st);   // N <= 128 only
+  if constexpr (SPLIT == 3) {   // three 64 KB stages up to 128 columns, two 96 KB stages beyond
+    if (g.N <= 128) return launch_gemm_tc_bn<A_KC, B_KC, 3, Epi, 128>(g, epi, nsplit, num_sms, st);
+    return launch_gemm_tc_bn<A_KC, B_KC, 3, Epi, 256>(g, epi, nsplit, num_sms, st);
+  }
   if constexpr (A_KC && SPLIT != 2) {
     const int bn = tc_pick_bn<A_KC, SPLIT>(g, nsplit, num_sms);
     if (bn == 64) return launch_gemm_tc_bn<A_KC, B_KC, SPLIT, Epi, 64>(g, epi, nsplit, num_sms, st);

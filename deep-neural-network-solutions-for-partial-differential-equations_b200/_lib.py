@@ -15,24 +15,37 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("FBSNN_LIB_PATH") or os.path.join(_HERE, "libfbsnn_b200.so")   # override: A/B of two builds
 SOURCES = ["fbsnn_api.cu", "mc_pricer.cu"]
-HEADERS = ["common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "gemm_tc16.cuh", "gemm_tc2g.cuh", "kernels.cuh", "philox.cuh",
+HEADERS = ["common.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "gemm_tc16.cuh", "gemm_tc2g.cuh", "gemm_chain.cuh", "kernels.cuh",
+           "philox.cuh",
            os.path.join("..", "..", "include", "fbsnn_b200.h")]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+NVCC_FLAGS = ["-O3", "-std=c++17", "--threads", "2", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
 _lock = threading.Lock()
 _lib = None
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _src_hash() -> str:
+    """Content hash of everything the library is built from (sources, headers, flags): unlike mtimes it survives a
+    copy of the tree (the GPU box gets a snapshot), so a shipped, matching .so is never rebuilt there."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for f in SOURCES + HEADERS:
         p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+        if os.path.exists(p):
+            with open(p, "rb") as fh:
+                h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != _src_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -48,6 +61,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(_src_hash())
     return LIB_PATH
 
 
@@ -58,6 +73,8 @@ def _declare(lib):
     lib.fbsnn_last_error.restype = c.c_char_p
     lib.fbsnn_last_error.argtypes = []
     lib.fbsnn_version.restype = c.c_int
+    lib.fbsnn_set_option.restype = c.c_int
+    lib.fbsnn_set_option.argtypes = [c.c_char_p, c.c_int]
     lib.fbsnn_launch_count.restype = c.c_longlong
     lib.fbsnn_launch_count.argtypes = []
     lib.fbsnn_dense_timing.restype = None
@@ -68,6 +85,9 @@ def _declare(lib):
     lib.fbsnn_dense_timing_entry.argtypes = [c.c_int, c.POINTER(c.c_double)]
     lib.fbsnn_debug_gemm.restype = c.c_int
     lib.fbsnn_debug_gemm.argtypes = [c.c_int] * 6 + [f32p, c.c_int, f32p, c.c_int, f32p, c.c_int, vp]
+    lib.fbsnn_debug_ws_offset.restype = c.c_int
+    lib.fbsnn_debug_ws_offset.argtypes = [c.POINTER(S.FbsnnSpec), i64, c.c_int, c.c_char_p, c.c_int, c.POINTER(i64),
+                                          c.POINTER(c.c_int)]
     lib.fbsnn_workspace_bytes.restype = c.c_int
     lib.fbsnn_workspace_bytes.argtypes = [c.POINTER(S.FbsnnSpec), i64, c.c_int, c.POINTER(sz)]
     lib.fbsnn_fetch_minibatch.restype = c.c_int
@@ -108,22 +128,30 @@ def _declare(lib):
     lib.mc_generate_paths.argtypes = [c.POINTER(S.McSpec), f32p, f32p, u64, u64, u64, f32p, vp]
 
 
-EXPORTS = ["fbsnn_last_error", "fbsnn_version", "fbsnn_launch_count", "fbsnn_dense_timing",
-           "fbsnn_dense_timing_read", "fbsnn_dense_timing_entry", "fbsnn_debug_gemm", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
+EXPORTS = ["fbsnn_last_error", "fbsnn_version", "fbsnn_set_option", "fbsnn_launch_count", "fbsnn_dense_timing",
+           "fbsnn_dense_timing_read", "fbsnn_dense_timing_entry", "fbsnn_debug_gemm", "fbsnn_debug_ws_offset", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
            "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_adam_step", "fbsnn_peer_buffer_floats", "fbsnn_peer_wait",
            "fbsnn_peer_allreduce_adam", "fbsnn_train_step", "mc_scratch_bytes", "mc_launch_count",
            "mc_basket_price", "mc_basket_price_delta", "mc_hjb_exact", "mc_generate_paths"]
 
 
 def load():
-    """dlopen the library (building it first if it is missing and nvcc is available)."""
+    """dlopen the library.  A missing or STALE library (a csrc / header file newer than the .so) is rebuilt first when
+    nvcc is available, so that an edited source can never silently run old kernels; the ABI version the ctypes struct
+    mirrors in spec.py were written against is checked after loading."""
     global _lib
     with _lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
+            from . import spec as S
+            have_nvcc = bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+            overridden = bool(os.environ.get("FBSNN_LIB_PATH"))
+            if not os.path.exists(LIB_PATH) or (_stale() and have_nvcc and not overridden):
                 build()
             lib = ctypes.CDLL(LIB_PATH)
             _declare(lib)
+            if lib.fbsnn_version() != S.ABI_VERSION:
+                raise RuntimeError(f"{LIB_PATH} reports ABI version {lib.fbsnn_version()}, spec.py expects "
+                                   f"{S.ABI_VERSION}: rebuild with _lib.build(force=True)")
             _lib = lib
     return _lib
 

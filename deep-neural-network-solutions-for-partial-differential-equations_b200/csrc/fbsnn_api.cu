@@ -14,6 +14,7 @@
 #include "gemm_tc2.cuh"
 #include "gemm_tc16.cuh"
 #include "gemm_tc2g.cuh"
+#include "gemm_chain.cuh"
 #include "kernels.cuh"
 
 namespace fbsnn {
@@ -69,6 +70,7 @@ struct Plan {
   size_t g[kMaxL + 2], a[kMaxL + 2], delta[kMaxL + 2], szz[kMaxL + 2], hd[kMaxL + 2], h[kMaxL + 2],
       ht[kMaxL + 2], hb[kMaxL + 2];
   size_t Bm[kMaxL + 2], Rm[kMaxL + 2], Bbar[kMaxL + 2], Sm[kMaxL + 2], nstate[kMaxL + 2];
+  size_t chain_col;   // per-CTA column-sum partials of the layer-chained T / B sweeps
   size_t total;
 };
 
@@ -186,6 +188,7 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
     p.part_wg = take(p.wg_stride * (p.nais ? 1 : p.L));   // FC: one partial buffer per layer, reduced together
     p.part_col = take((size_t)kMaxColJobs * std::max(p.col_blocks, 256) * 1024);   // 256 >= CTAs of the tcgen05 grid
     p.part_gsq = take(p.gsq_blocks);
+    if (p.tf32 && !p.nais) p.chain_col = take((size_t)num_sms() * chain::kMaxLinks * 2 * 1024);
     if (p.nais)
       for (int l = 2; l <= p.L; ++l) {
         const size_t hh = (size_t)p.H[l] * p.H[l];
@@ -499,9 +502,221 @@ static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* 
   return 0;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Layer-chained sweeps (gemm_chain.cuh): FC networks on the tensor-core variants whose widths tile into 32-column
+// chunks.  Option "chain": 0 = per-layer launches only, 1 = chained sweeps once the row tiles fill the chip (the small-M
+// steps keep the narrow-tile per-layer launches that spread 40 row tiles over all SMs), 2 = always when eligible.
+// ----------------------------------------------------------------------------------------------------------------
+static int g_opt_chain = -1;
+static int chain_mode() {
+  if (g_opt_chain < 0) {
+    const char* e = getenv("FBSNN_CHAIN");
+    g_opt_chain = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return g_opt_chain;
+}
+static bool chain_eligible(const FbsnnSpec* s, const Plan& p) {
+  if (chain_mode() == 0 || p.nais || !p.tf32) return false;
+  if (p.ldx % 32 || p.ldx > 256 || p.L + 1 > chain::kMaxLinks) return false;
+  for (int l = 1; l <= p.L; ++l)
+    if (p.H[l] % 32 || p.H[l] < 64 || p.H[l] > 256) return false;
+  if (chain_mode() == 1 && p.rows < (long long)num_sms() * 128) return false;
+  return true;
+}
+static bool row_map(CUtensorMap* m, const float* base, int width, long long rows) {
+  return tc::make_map(m, base, width, rows, width, 32, 128, false);
+}
+// weight operand of the MMA fed by link i: layer `l` used as W^T (b_mn = false: W[n][k], F / T) or as W (A / B)
+static bool weight_maps(const Plan& p, const Net& n, float* ws, int l, bool b_mn, chain::Maps& m, int i) {
+  const int K = l == 1 ? p.ldx : p.H[l - 1];   // columns of layer l's matrix (H_l x K, row-major, ld = K)
+  const int Hl = p.H[l];
+  const float* hi = p.x3 ? ws + p.Whi[l] : n.W[l];
+  const float* lo = p.x3 ? ws + p.Wlo[l] : n.W[l];
+  bool ok;
+  if (!b_mn) {   // out = A[rows x K] * W^T: B[n = H_l][k]
+    ok = tc::make_map(&m.whi[i], hi, K, Hl, K, 32, Hl, false) && tc::make_map(&m.wlo[i], lo, K, Hl, K, 32, Hl, false);
+  } else {       // out = A[rows x H_l] * W: B[k = H_l][n = K]
+    ok = tc::make_map(&m.whi[i], hi, K, Hl, K, 32, 32, true) && tc::make_map(&m.wlo[i], lo, K, Hl, K, 32, 32, true);
+  }
+  return ok;
+}
+static void chain_timing_begin(int& slot, const chain::Args& a, const char* what, cudaStream_t st) {
+  slot = -1;
+  if (!(g_timing && g_ntimed < kMaxTimed)) return;
+  slot = g_ntimed++;
+  if (!g_ev0[slot]) cudaEventCreate(&g_ev0[slot]), cudaEventCreate(&g_ev1[slot]);
+  double flops = 0, arrays = 0;   // arrays in units of (rows x 1 column) floats
+  for (int i = 0; i < a.nlinks; ++i) {
+    const chain::LinkD& L = a.link[i];
+    if (L.feeds) flops += 2.0 * (double)a.rows * L.width * L.n_next;
+    arrays += (double)L.width * ((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0) + (L.out0 ? 1 : 0) + (L.out2 ? 1 : 0));
+  }
+  g_flops[slot] = flops;
+  g_bytes[slot] = 4.0 * (double)a.rows * arrays;
+  g_timed_tc[slot] = true;
+  g_timed_what[slot] = what;
+  cudaEventRecord(g_ev0[slot], st);
+}
+template <int SWEEP>
+static int chain_launch(const FbsnnSpec* s, const chain::Maps& m, const chain::Args& a, const char* what, cudaStream_t st) {
+  int slot;
+  chain_timing_begin(slot, a, what, st);
+  ++g_launches;
+  const cudaError_t e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chain<SWEEP, true>(m, a, num_sms(), st)
+                                                           : chain::launch_chain<SWEEP, false>(m, a, num_sms(), st);
+  if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
+  if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "chained sweep %s: %s", what, cudaGetErrorString(e));
+  static int debug = -1;
+  if (debug < 0) debug = getenv("FBSNN_CHAIN_DEBUG") ? 1 : 0;
+  if (debug) {   // bring-up aid: localise a faulting sweep (never set while capturing a graph)
+    const cudaError_t e2 = cudaStreamSynchronize(st);
+    fprintf(stderr, "[fbsnn] chained sweep %s (%d links, %d tiles): %s\n", what, a.nlinks, a.ntiles, cudaGetErrorString(e2));
+    if (e2 != cudaSuccess) return fail(FBSNN_E_CUDA, "chained sweep %s failed: %s", what, cudaGetErrorString(e2));
+  }
+  return 0;
+}
+static int internal_act(const FbsnnSpec* s) {
+  int act = s->act_kind;
+  if (s->precision == FBSNN_PREC_TF32X3 && act == FBSNN_ACT_SINE) act = kActSineCW;
+  if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_SINE) act = kActSineFast;
+  if (s->precision == FBSNN_PREC_TF32 && act == FBSNN_ACT_TANH) act = kActTanhFast;
+  return act;
+}
+static void chain_base(const FbsnnSpec* s, const Plan& p, const Net& n, chain::Args& a) {
+  memset(&a, 0, sizeof(a));
+  a.rows = (int)p.rows, a.ntiles = (int)((p.rows + 127) / 128), a.act = internal_act(s);
+  a.wout = n.wout, a.bout = n.bout;
+  static int ablate = -1;
+  if (ablate < 0) {
+    const char* e = getenv("FBSNN_CHAIN_ABLATE");
+    ablate = e ? atoi(e) : 0;
+  }
+  a.ablate = ablate;
+}
+
+// F and A sweeps as two launches; leaves g_l, a_l, delta_l (, s_l for l < L), Y and Du_full in the workspace
+static int chain_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, bool with_grad, cudaStream_t st) {
+  const long long R = p.rows;
+  const int L = p.L;
+  {
+    chain::Maps m;
+    chain::Args a;
+    chain_base(s, p, n, a);
+    a.nlinks = L + 1, a.Y = ws + p.Y;
+    bool ok = true;
+    a.link[0] = chain::LinkD{p.ldx, p.H[1], chain::LINK_FIRST, 1, 0, 0, 0, 1, 0, 0};
+    ok = ok && row_map(&m.in0[0], ws + p.xin, p.ldx, R) && weight_maps(p, n, ws, 1, false, m, 0);
+    for (int l = 1; l <= L; ++l) {
+      const bool last = l == L;
+      a.link[l] = chain::LinkD{p.H[l], last ? 0 : p.H[l + 1], (unsigned char)(last ? chain::LINK_LAST : chain::LINK_MID),
+                               0, 0, 1, 1, (unsigned char)(last ? 0 : 1), 0, 0};
+      a.bias[l] = n.b[l];
+      ok = ok && row_map(&m.out0[l], ws + p.g[l], p.H[l], R) && row_map(&m.out2[l], ws + p.a[l], p.H[l], R);
+      if (!last) ok = ok && weight_maps(p, n, ws, l + 1, false, m, l);
+    }
+    if (!ok) return fail(FBSNN_E_CUDA, "chained F sweep: tensor map encoding failed");
+    int rc = chain_launch<chain::SWEEP_F>(s, m, a, "F*", st);
+    if (rc) return rc;
+  }
+  {
+    chain::Maps m;
+    chain::Args a;
+    chain_base(s, p, n, a);
+    a.nlinks = L + 1, a.with_s = with_grad ? 1 : 0;
+    bool ok = true;
+    // link 0: delta_L = wout * a_L
+    a.link[0] = chain::LinkD{p.H[L], L >= 2 ? p.H[L - 1] : p.ldx, chain::LINK_FIRST, 1, 0, 1, 0, 1, 1, 0};
+    ok = ok && row_map(&m.in0[0], ws + p.a[L], p.H[L], R) && row_map(&m.out0[0], ws + p.delta[L], p.H[L], R) &&
+         weight_maps(p, n, ws, L, true, m, 0);
+    for (int k = 1; k <= L - 1; ++k) {
+      const int l = L - k;
+      a.link[k] = chain::LinkD{p.H[l], l >= 2 ? p.H[l - 1] : p.ldx, chain::LINK_MID, 1, (unsigned char)(with_grad ? 1 : 0), 1,
+                               (unsigned char)(with_grad ? 1 : 0), 1, 1, 0};
+      ok = ok && row_map(&m.in0[k], ws + p.a[l], p.H[l], R) && row_map(&m.out0[k], ws + p.delta[l], p.H[l], R) &&
+           weight_maps(p, n, ws, l, true, m, k);
+      if (with_grad) ok = ok && row_map(&m.in2[k], ws + p.g[l], p.H[l], R) && row_map(&m.out2[k], ws + p.szz[l], p.H[l], R);
+    }
+    a.link[L] = chain::LinkD{p.ldx, 0, chain::LINK_LAST, 0, 0, 1, 0, 0, 0, 0};
+    ok = ok && row_map(&m.out0[L], ws + p.zf, p.ldx, R);
+    if (!ok) return fail(FBSNN_E_CUDA, "chained A sweep: tensor map encoding failed");
+    int rc = chain_launch<chain::SWEEP_A>(s, m, a, "A*", st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// T and B sweeps as two launches + the column-sum finish (bias and output-weight gradients)
+static int chain_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, float* grads, cudaStream_t st) {
+  const long long R = p.rows;
+  const int L = p.L;
+  chain::ColFinJobs fin{};
+  float* colacc = ws + p.chain_col;
+  {
+    chain::Maps m;
+    chain::Args a;
+    chain_base(s, p, n, a);
+    a.nlinks = L + 1, a.ybar = ws + p.ybar, a.colacc = colacc;
+    bool ok = true;
+    a.link[0] = chain::LinkD{p.ldx, p.H[1], chain::LINK_FIRST, 1, 0, 0, 0, 1, 0, 0};
+    ok = ok && row_map(&m.in0[0], ws + p.V, p.ldx, R) && weight_maps(p, n, ws, 1, false, m, 0);
+    for (int l = 1; l <= L - 1; ++l) {
+      a.link[l] = chain::LinkD{p.H[l], p.H[l + 1], chain::LINK_MID, 1, 1, 1, 1, 1, 0, 0};
+      ok = ok && row_map(&m.in0[l], ws + p.a[l], p.H[l], R) && row_map(&m.in2[l], ws + p.szz[l], p.H[l], R) &&
+           row_map(&m.out0[l], ws + p.hd[l], p.H[l], R) && row_map(&m.out2[l], ws + p.szz[l], p.H[l], R) &&
+           weight_maps(p, n, ws, l + 1, false, m, l);
+    }
+    // last hidden layer: zbar_L (stored, bias_L gradient) and dbar a + ybar g (output-weight gradient, column sums only)
+    a.link[L] = chain::LinkD{p.H[L], 0, chain::LINK_LAST, 1, 1, 1, 0, 0, 0, 3};
+    ok = ok && row_map(&m.in0[L], ws + p.a[L], p.H[L], R) && row_map(&m.in2[L], ws + p.g[L], p.H[L], R) &&
+         row_map(&m.out0[L], ws + p.szz[L], p.H[L], R);
+    if (!ok) return fail(FBSNN_E_CUDA, "chained T sweep: tensor map encoding failed");
+    int rc = chain_launch<chain::SWEEP_T>(s, m, a, "T*", st);
+    if (rc) return rc;
+    fin.job[fin.njobs++] = chain::ColFinJob{L, 0, p.H[L], grads + s->off_b[L]};
+    fin.job[fin.njobs++] = chain::ColFinJob{L, 1, p.H[L], grads + s->off_W[L + 1]};
+    fin.nblk = std::min(a.ntiles, num_sms());
+  }
+  if (L >= 2) {
+    chain::Maps m;
+    chain::Args a;
+    chain_base(s, p, n, a);
+    a.nlinks = L, a.colacc = colacc;
+    bool ok = true;
+    a.link[0] = chain::LinkD{p.H[L], p.H[L - 1], chain::LINK_FIRST, 1, 0, 0, 0, 1, 1, 0};
+    ok = ok && row_map(&m.in0[0], ws + p.szz[L], p.H[L], R) && weight_maps(p, n, ws, L, true, m, 0);
+    for (int k = 1; k <= L - 1; ++k) {
+      const int l = L - k;
+      const bool last = l == 1;
+      a.link[k] = chain::LinkD{p.H[l], last ? 0 : p.H[l - 1], (unsigned char)(last ? chain::LINK_LAST : chain::LINK_MID), 1, 1, 1,
+                               0, (unsigned char)(last ? 0 : 1), 1, 1};
+      ok = ok && row_map(&m.in0[k], ws + p.a[l], p.H[l], R) && row_map(&m.in2[k], ws + p.szz[l], p.H[l], R) &&
+           row_map(&m.out0[k], ws + p.szz[l], p.H[l], R);
+      if (!last) ok = ok && weight_maps(p, n, ws, l, true, m, k);
+      fin.job[fin.njobs++] = chain::ColFinJob{k, 0, p.H[l], grads + s->off_b[l]};
+    }
+    if (!ok) return fail(FBSNN_E_CUDA, "chained B sweep: tensor map encoding failed");
+    int rc = chain_launch<chain::SWEEP_B>(s, m, a, "B*", st);
+    if (rc) return rc;
+  }
+  chain::chain_colsum_finish_kernel<<<dim3(1, fin.njobs), 256, 0, st>>>(colacc, fin);
+  LAUNCH_CHECK("chain_colsum_finish");
+  return 0;
+}
+
 // F and A sweeps over `rows` rows whose inputs are already in ws[xin]; leaves Y in ws[Y], Du_full in ws[zf].
 static int sweeps_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float* ws, bool with_grad, cudaStream_t st) {
   const int R = (int)p.rows;
+  if (chain_eligible(s, p)) {
+    int rc = chain_forward(s, p, n, ws, with_grad, st);
+    if (rc) return rc;
+    if (s->clamp_u) {
+      const long long thr = p.rows * 32;
+      clamp_u_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(ws + p.Y, ws + p.zf, p.ldx, p.rows, ws + p.umask);
+      LAUNCH_CHECK("clamp_u");
+    }
+    return 0;
+  }
   int act = s->act_kind;
   // 3xTF32 keeps the fp32-grade sine (Cody-Waite + minimax polynomials, ~22 instructions): the F-sweep epilogue is
   // instruction-bound on it (3.3 ms per layer vs 2.8 ms with the MUFU form, measured), the price of fp32-grade results
@@ -627,8 +842,13 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
   auto col_part = [&](int job) { return ws + p.part_col + (size_t)job * col_slots * 1024; };   // job l = bias of layer l
   bool fused_bias[kMaxL + 2] = {};
   int fused_grid[kMaxL + 2] = {};
+  const bool chained = chain_eligible(s, p);
+  if (chained) {
+    int rc = chain_backward(s, p, n, ws, grads, st);
+    if (rc) return rc;
+  }
   // ---- T sweep -----------------------------------------------------------------------------------------
-  for (int l = 1; l <= p.L; ++l) {
+  for (int l = 1; l <= p.L && !chained; ++l) {
     GemmArgs g{};
     g.M = R, g.N = p.H[l], g.Nb = p.H[l], g.kchunk = 0;
     if (l == 1) {
@@ -656,7 +876,7 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     if (rc) return rc;
   }
   // ---- B sweep -----------------------------------------------------------------------------------------
-  for (int l = p.L; l >= 2; --l) {
+  for (int l = p.L; l >= 2 && !chained; --l) {
     GemmArgs g{};
     g.M = R, g.N = p.H[l - 1], g.Nb = p.H[l - 1], g.kchunk = 0, g.nseg = 1;
     g.seg[0] = GemmSeg{ws + p.szz[l], n.W[l], p.H[l], p.H[l - 1], p.H[l]};
@@ -710,6 +930,7 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     reduce_partials_batched_kernel<<<dim3((maxn + 255) / 256, red.njobs), 256, 0, st>>>(red);
     LAUNCH_CHECK("reduce_partials_batched");
   }
+  if (chained) return 0;   // bias and output-weight gradients came out of the chained sweeps' fused column sums
   // ---- bias / output-layer gradients: column sums -----------------------------------------------------------
   ColJobs js{};
   js.rows = p.rows, js.rows_per_block = p.col_rows_per_block, js.max_width = 1024;
@@ -842,7 +1063,18 @@ using namespace fbsnn;
 extern "C" {
 
 const char* fbsnn_last_error(void) { return g_err; }
-int fbsnn_version(void) { return 101; }
+int fbsnn_version(void) { return 102; }
+// Run-time switches (tests and A/B measurements): "chain" = 0 | 1 | 2 (layer-chained sweeps: off / auto / always when
+// eligible).  Returns the previous value, or FBSNN_E_BADARG for an unknown name.
+int fbsnn_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "chain")) {
+    const int old = chain_mode();
+    if (value < 0 || value > 2) return fail(FBSNN_E_BADARG, "option chain takes 0, 1 or 2");
+    g_opt_chain = value;
+    return old;
+  }
+  return fail(FBSNN_E_BADARG, "unknown option %s", name ? name : "(null)");
+}
 long long fbsnn_launch_count(void) { return g_launches; }
 void fbsnn_dense_timing(int enable) { g_timing = enable != 0; g_ntimed = 0; }
 // Sums the recorded dense-layer launches (caller has synchronised): out = {n_launches, total ms, total FLOPs,
@@ -934,6 +1166,37 @@ int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const 
     else return fail(FBSNN_E_UNSUPPORTED, "layout");
   }
   if (err != cudaSuccess) return fail(FBSNN_E_CUDA, "debug gemm: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+// Test hook: offset (in floats) of a named per-row array of the workspace plan, so that a test can compare the arrays
+// two dispatch variants leave behind.  name in {"xin","Y","zf","V","ybar","g","a","delta","szz","hd"}; layer 1..L for
+// the per-layer arrays.  Returns the row width in *width_out.
+int fbsnn_debug_ws_offset(const FbsnnSpec* spec, int64_t n_paths, int with_grad, const char* name, int layer,
+                          int64_t* offset_out, int* width_out) {
+  int rc = validate(spec);
+  if (rc) return rc;
+  if (n_paths < 1 || !name || !offset_out || !width_out) return fail(FBSNN_E_BADARG, "debug_ws_offset: bad argument");
+  Plan p;
+  make_plan(spec, (long long)n_paths * (spec->N + 1), with_grad != 0, p);
+  const bool per_layer = !strcmp(name, "g") || !strcmp(name, "a") || !strcmp(name, "delta") || !strcmp(name, "szz") || !strcmp(name, "hd");
+  if (per_layer && (layer < 1 || layer > p.L)) return fail(FBSNN_E_BADARG, "debug_ws_offset: layer outside 1..L");
+  size_t off;
+  int w;
+  if (!strcmp(name, "xin")) off = p.xin, w = p.ldx;
+  else if (!strcmp(name, "Y")) off = p.Y, w = 1;
+  else if (!strcmp(name, "zf")) off = p.zf, w = p.ldx;
+  else if (!strcmp(name, "V")) off = p.V, w = p.ldx;
+  else if (!strcmp(name, "ybar")) off = p.ybar, w = 1;
+  else if (!strcmp(name, "g")) off = p.g[layer], w = p.H[layer];
+  else if (!strcmp(name, "a")) off = p.a[layer], w = p.H[layer];
+  else if (!strcmp(name, "delta")) off = p.delta[layer], w = p.H[layer];
+  else if (!strcmp(name, "szz")) off = p.szz[layer], w = p.H[layer];
+  else if (!strcmp(name, "hd")) off = p.hd[layer], w = p.H[layer];
+  else return fail(FBSNN_E_BADARG, "debug_ws_offset: unknown array %s", name);
+  if (!with_grad && (!strcmp(name, "V") || !strcmp(name, "ybar") || !strcmp(name, "szz") || !strcmp(name, "hd")))
+    return fail(FBSNN_E_BADARG, "debug_ws_offset: %s exists only in the training plan", name);
+  *offset_out = (int64_t)off, *width_out = w;
   return 0;
 }
 

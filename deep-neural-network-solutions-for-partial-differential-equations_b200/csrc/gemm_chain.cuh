@@ -1,0 +1,490 @@
+// Layer-chained sweep kernel (FC networks, tcgen05 variants): ONE persistent launch runs a whole sweep
+// (F, A, T or B of fbsnn_api.cu) over all of its layers.  A 128-row tile walks through the layers on chip: the
+// epilogue of layer l turns the accumulator (TMEM) into the NEXT layer's A operand directly in shared memory, 32
+// columns (= one k-block) at a time, so the carried activation never travels through HBM and the next layer's MMAs
+// start as soon as the first k-block exists.  Every row array a LATER sweep needs is read / written by TMA from / to
+// the same swizzled 16 KB chunk buffers (no register-level global traffic, no transposes):
+//
+//   link i = "epilogue stage" between MMA i and MMA i+1.  For every 32-column chunk of the link:
+//     input producer   TMA-loads up to two row-array chunks (e.g. a_l, s_l) into buf0 / buf2 of an A-ring stage
+//     epilogue group   (4 warps = 128 rows, lane = row) reads the accumulator chunk with tcgen05.ld, combines it with
+//                      the loaded chunks, writes the results back IN PLACE: buf0 = next A operand (+ buf1 = its
+//                      3xTF32 low part), buf2 = second output; canonical K-major SWIZZLE_128B layout, which is at
+//                      the same time what tcgen05.mma reads and what a TMA store expects
+//     MMA warp         issues the k-block of MMA i+1 (A = buf0 / buf1, B = weight ring fed by the weight producer)
+//     store warp       TMA-stores buf0 / buf2 to the row arrays of HBM
+//   The two accumulators (2 x 256 TMEM columns) alternate between consecutive MMAs, so the epilogue of link i
+//   overlaps MMA i+1 chunk by chunk.
+//
+// Warps: 0 weight producer | 1 MMA issuer (owns TMEM) | 2 input producer | 3 store | 4.. epilogue groups.
+// Shared memory (3xTF32): 2 weight stages x (W_hi 32 KB + W_lo 32 KB) + 2 A stages x 3 x 16 KB = 224 KB;
+// (TF32): 4 weight stages x 32 KB + 3 A stages x 2 x 16 KB = 224 KB.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace fbsnn {
+namespace chain {
+
+using tc::smem_u32;
+
+constexpr int kMaxLinks = FBSNN_MAX_HIDDEN + 1;
+enum { SWEEP_F = 0, SWEEP_A = 1, SWEEP_T = 2, SWEEP_B = 3 };
+enum { LINK_FIRST = 0, LINK_MID = 1, LINK_LAST = 2 };
+constexpr int CHUNK_BYTES = 128 * 32 * 4;   // 128 rows x 32 fp32 columns
+
+struct LinkD {
+  int width;    // columns of this link's row arrays (multiple of 32, <= 256)
+  int n_next;   // N of the MMA this link feeds (0: none)
+  unsigned char kind, in0, in2, out0, out2, feeds, b_mn, colsum;   // colsum: bit 0 = buf0, bit 1 = buf2
+};
+struct Maps {
+  CUtensorMap in0[kMaxLinks], in2[kMaxLinks], out0[kMaxLinks], out2[kMaxLinks], whi[kMaxLinks], wlo[kMaxLinks];
+};
+struct Args {
+  int nlinks, rows, ntiles, act, with_s;
+  int ablate;   // measurement only (FBSNN_CHAIN_ABLATE): 1 no TMA stores, 2 no input loads, 4 no epilogue math, 8 no MMAs, 16 no weight loads
+  LinkD link[kMaxLinks];
+  const float* bias[kMaxLinks];   // F: bias of the layer whose pre-activation link i receives
+  const float* wout;
+  const float* bout;
+  const float* ybar;              // T
+  float* Y;                       // F: output head
+  float* colacc;                  // T / B: [grid][kMaxLinks][2][4][256] per-CTA column sums (row quarter q kept apart)
+};
+
+template <bool X3>
+struct Cfg {
+  static constexpr int W_STAGE = X3 ? 65536 : 32768;
+  static constexpr int W_STAGES = X3 ? 2 : 4;
+  static constexpr int A_BUFS = X3 ? 3 : 2;                  // [buf0][buf1 = lo (3xTF32 only)][buf2]
+  static constexpr int A_STAGE = A_BUFS * CHUNK_BYTES;
+  static constexpr int A_STAGES = X3 ? 2 : 3;
+  static constexpr int GROUPS = A_STAGES;                    // epilogue groups of 4 warps
+  static constexpr int EPI_WARP0 = 4;
+  static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + 4 * GROUPS);
+  static constexpr int B2_OFF = (A_BUFS - 1) * CHUNK_BYTES;  // byte offset of buf2 inside a stage
+  static constexpr int EXTRA_BYTES = 2048;                   // barriers, TMEM slot, head partials
+  static constexpr int SMEM_BYTES = W_STAGES * W_STAGE + A_STAGES * A_STAGE + EXTRA_BYTES + 1024 /*align*/;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// bounded wait that says WHO starved before trapping (role: 0 weights, 1 MMA, 2 inputs, 3 store, 4 epilogue)
+__device__ __noinline__ void chain_timeout(int role, int what, int link, int chunk) {
+  printf("fbsnn chain kernel: block %d thread %d role %d wait %d link %d chunk %d timed out\n", (int)blockIdx.x,
+         (int)threadIdx.x, role, what, link, chunk);
+  asm volatile("trap;");
+}
+__device__ __forceinline__ void cwait(uint64_t* b, uint32_t parity, int role, int what, int link, int chunk) {
+  uint32_t ok = 0, spins = 0;
+  const uint32_t addr = smem_u32(b);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > tc::kSpinLimit) chain_timeout(role, what, link, chunk);
+  }
+}
+__device__ __forceinline__ float lo_part(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <int SWEEP, bool X3>
+__global__ void __launch_bounds__(Cfg<X3>::NUM_THREADS, 1)
+chain_kernel(const __grid_constant__ Maps tm, const Args a) {
+  using C = Cfg<X3>;
+  constexpr int AS = C::A_STAGES, WS = C::W_STAGES, G = C::GROUPS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wring = smem;
+  uint8_t* aring = smem + WS * C::W_STAGE;
+  uint8_t* extra = aring + AS * C::A_STAGE;
+  uint64_t* bars = (uint64_t*)extra;
+  uint64_t* w_full = bars;           // [WS]  weight k-block landed
+  uint64_t* w_empty = bars + 4;      // [WS]  MMAs that read it completed
+  uint64_t* in_full = bars + 8;      // [AS]  input chunks landed (or: stage handed to the epilogue)
+  uint64_t* a_ready = bars + 12;     // [AS]  epilogue group has written the chunk (4 warp arrivals)
+  uint64_t* a_free = bars + 16;      // [AS]  MMAs that read the chunk completed + TMA stores have read it
+  uint64_t* acc_full = bars + 20;    // [2]
+  uint64_t* acc_empty = bars + 22;   // [2]   all epilogue warps have drained the accumulator
+  uint32_t* tmem_slot = (uint32_t*)(bars + 24);
+  float* ypart = (float*)(extra + 256);   // [G][128] head partial sums (F sweep)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < a.nlinks; ++i) {
+      const LinkD& L = a.link[i];
+      if (L.in0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.in0[i]) : "memory");
+      if (L.in2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.in2[i]) : "memory");
+      if (L.out0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.out0[i]) : "memory");
+      if (L.out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.out2[i]) : "memory");
+      if (L.feeds) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.whi[i]) : "memory");
+        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.wlo[i]) : "memory");
+      }
+    }
+    for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < AS; ++i) tc::mbar_init(&in_full[i], 1), tc::mbar_init(&a_ready[i], 4), tc::mbar_init(&a_free[i], 2);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], 4 * G);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  tc::pdl_trigger();
+  tc::pdl_wait();
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t ws = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          if (!L.feeds) continue;
+          const int nch = L.width >> 5, N = L.n_next;
+          const uint32_t bytes = (uint32_t)N * 128u * (X3 ? 2u : 1u);
+          for (int j = 0; j < nch; ++j) {
+            cwait(&w_empty[ws], wph ^ 1, 0, 0, i, j);
+            uint8_t* dst = wring + ws * C::W_STAGE;
+            if (a.ablate & 16) {
+              tc::mbar_arrive(&w_full[ws]);
+            } else {
+              tc::mbar_expect_tx(&w_full[ws], bytes);
+              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
+                for (int c = 0; c < N / 32; ++c) {
+                  tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
+                  if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
+                }
+              } else {        // W[n][k] (k contiguous): one N x 32 box
+                tc::tma_load_2d(dst, &tm.whi[i], &w_full[ws], 32 * j, 0);
+                if (X3) tc::tma_load_2d(dst + 32768, &tm.wlo[i], &w_full[ws], 32 * j, 0);
+              }
+            }
+            if (++ws == WS) ws = 0, wph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== input producer =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int m0 = tile * 128;
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          const int nch = L.width >> 5;
+          for (int j = 0; j < nch; ++j) {
+            cwait(&a_free[s], ph ^ 1, 2, 0, i, j);
+            uint8_t* st = aring + s * C::A_STAGE;
+            if ((L.in0 || L.in2) && !(a.ablate & 2)) {
+              tc::mbar_expect_tx(&in_full[s], (uint32_t)CHUNK_BYTES * (uint32_t)((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0)));
+              if (L.in0) tc::tma_load_2d(st, &tm.in0[i], &in_full[s], 32 * j, m0);
+              if (L.in2) tc::tma_load_2d(st + C::B2_OFF, &tm.in2[i], &in_full[s], 32 * j, m0);
+            } else {
+              tc::mbar_arrive(&in_full[s]);
+            }
+            if (++s == AS) s = 0, ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0, ws = 0, wph = 0, mm = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          const int nch = L.width >> 5;
+          const uint32_t acc = mm & 1;
+          uint32_t idesc = 0;
+          if (L.feeds) {
+            cwait(&acc_empty[acc], ((mm >> 1) & 1) ^ 1, 1, 0, i, 0);
+            tc::tc_fence_after();
+            idesc = tc::make_idesc(L.n_next, false, L.b_mn != 0);
+          }
+          const uint32_t tmem_d = tmem_base + acc * 256;
+          for (int j = 0; j < nch; ++j) {
+            cwait(&a_ready[s], ph, 1, 1, i, j);
+            if (L.feeds) {
+              cwait(&w_full[ws], wph, 1, 2, i, j);
+              tc::tc_fence_after();
+              if (!(a.ablate & 8)) {
+              const uint32_t a0 = smem_u32(aring + s * C::A_STAGE);
+              const uint32_t alo = a0 + CHUNK_BYTES;
+              const uint32_t b0 = smem_u32(wring + ws * C::W_STAGE);
+              const uint32_t blo = b0 + 32768;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = tc::make_desc(a0 + k * 32, 16, 1024, 2);
+                const uint64_t db = L.b_mn ? tc::make_desc(b0 + k * 1024, 4096, 512, 1) : tc::make_desc(b0 + k * 32, 16, 1024, 2);
+                if (X3) {
+                  const uint64_t dal = tc::make_desc(alo + k * 32, 16, 1024, 2);
+                  const uint64_t dbl = L.b_mn ? tc::make_desc(blo + k * 1024, 4096, 512, 1) : tc::make_desc(blo + k * 32, 16, 1024, 2);
+                  tc::umma_tf32(tmem_d, dal, db, idesc, (j | k) ? 1u : 0u);
+                  tc::umma_tf32(tmem_d, da, dbl, idesc, 1u);
+                  tc::umma_tf32(tmem_d, da, db, idesc, 1u);
+                } else {
+                  tc::umma_tf32(tmem_d, da, db, idesc, (j | k) ? 1u : 0u);
+                }
+              }
+              }
+              tc::umma_commit(&w_empty[ws]);
+              if (++ws == WS) ws = 0, wph ^= 1;
+            }
+            tc::umma_commit(&a_free[s]);   // (also for chunks nothing reads: commits complete in order)
+            if (++s == AS) s = 0, ph ^= 1;
+          }
+          if (L.feeds) {
+            tc::umma_commit(&acc_full[acc]);
+            ++mm;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== store warp =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int m0 = tile * 128;
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          const int nch = L.width >> 5;
+          for (int j = 0; j < nch; ++j) {
+            cwait(&a_ready[s], ph, 3, 0, i, j);
+            const uint8_t* st = aring + s * C::A_STAGE;
+            const bool do_store = (L.out0 || L.out2) && !(a.ablate & 1);
+            if (do_store && L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
+            if (do_store && L.out2) tma_store_2d(&tm.out2[i], st + C::B2_OFF, 32 * j, m0);
+            if (do_store) {
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            tc::mbar_arrive(&a_free[s]);
+            if (++s == AS) s = 0, ph ^= 1;
+          }
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
+    }
+  } else {
+    // ===================== epilogue groups =====================
+    const int e = warp - C::EPI_WARP0;
+    const int q = warp & 3;          // TMEM lane quarter
+    const int grp = e >> 2;
+    const int rt = q * 32 + lane;    // row inside the tile
+    const int rsw = rt & 7;
+    uint32_t cc = 0, mmr = 0;
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, first_tile = false) {
+      const int row = tile * 128 + rt;
+      const bool valid = row < a.rows;
+      float yb = 0.f, yacc = 0.f;
+      if (SWEEP == SWEEP_T) yb = valid ? __ldg(a.ybar + row) : 0.f;
+      for (int i = 0; i < a.nlinks; ++i) {
+        const LinkD& L = a.link[i];
+        const int nch = L.width >> 5;
+        const bool has_acc = L.kind != LINK_FIRST;
+        const uint32_t acc = mmr & 1;
+        if (has_acc) {
+          cwait(&acc_full[acc], (mmr >> 1) & 1, 4, 0, i, 0);
+          tc::tc_fence_after();
+        }
+        for (int j = 0; j < nch; ++j) {
+          if (j % G != grp) continue;
+          const uint32_t cj = cc + (uint32_t)j;
+          const uint32_t s = cj % AS, ph = (cj / AS) & 1;
+          cwait(&in_full[s], ph, 4, 1, i, j);
+          float* b0 = (float*)(aring + s * C::A_STAGE);
+          float* b1 = b0 + CHUNK_BYTES / 4;
+          float* b2 = (float*)(aring + s * C::A_STAGE + C::B2_OFF);
+          uint32_t v[32];
+          if (has_acc) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (uint32_t)(32 * j);
+            FBSNN_TMEM_LD32(taddr, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+          const int c0 = 32 * j;
+          const bool want_lo = X3 && L.feeds;
+          if (!(a.ablate & 4))
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int off = rt * 32 + ((u ^ rsw) << 2);
+            float x0[4] = {0.f, 0.f, 0.f, 0.f}, x2[4] = {0.f, 0.f, 0.f, 0.f};
+            if (L.in0) { const float4 t = ld4(b0 + off); x0[0] = t.x, x0[1] = t.y, x0[2] = t.z, x0[3] = t.w; }
+            if (L.in2) { const float4 t = ld4(b2 + off); x2[0] = t.x, x2[1] = t.y, x2[2] = t.z, x2[3] = t.w; }
+            const float ac[4] = {__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
+                                 __uint_as_float(v[4 * u + 3])};
+            float o0[4], o2[4];
+            bool w0 = true, w2 = false;
+            if constexpr (SWEEP == SWEEP_F) {
+              if (L.kind == LINK_FIRST) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o0[t] = x0[t];
+                w0 = false;
+              } else {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias[i] + c0 + 4 * u));
+                const float z[4] = {ac[0] + b.x, ac[1] + b.y, ac[2] + b.z, ac[3] + b.w};
+                act_ga4(a.act, z, o0, o2);
+                w2 = true;
+                if (L.kind == LINK_LAST) {
+                  const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
+                  yacc = fmaf(o0[0], w.x, fmaf(o0[1], w.y, fmaf(o0[2], w.z, fmaf(o0[3], w.w, yacc))));
+                }
+              }
+            } else if constexpr (SWEEP == SWEEP_A) {
+              if (L.kind == LINK_FIRST) {          // delta_L = wout * a_L
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
+                o0[0] = w.x * x0[0], o0[1] = w.y * x0[1], o0[2] = w.z * x0[2], o0[3] = w.w * x0[3];
+              } else if (L.kind == LINK_MID) {     // ht = acc; delta = ht * a; s = ht * c(g, a)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  o0[t] = ac[t] * x0[t];
+                  o2[t] = ac[t] * act_c(a.act, x2[t], x0[t]);
+                }
+                w2 = a.with_s != 0;
+              } else {                             // Du
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o0[t] = ac[t];
+              }
+            } else if constexpr (SWEEP == SWEEP_T) {
+              if (L.kind == LINK_FIRST) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o0[t] = x0[t];
+                w0 = false;
+              } else if (L.kind == LINK_MID) {     // dbar = acc; hd = dbar * a; zz = dbar * s
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o0[t] = ac[t] * x0[t], o2[t] = ac[t] * x2[t];
+                w2 = true;
+              } else {   // last hidden layer: zbar = ybar wout a + dbar (wout c);  wg = dbar a + ybar g  (column sums only)
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
+                const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float av = x0[t], gv = x2[t];
+                  const float sv = w[t] * act_c(a.act, gv, av);
+                  const float zz = ac[t] * sv;
+                  o0[t] = zz + yb * w[t] * av;
+                  o2[t] = ac[t] * av + yb * gv;
+                }
+                w2 = true;
+              }
+            } else {
+              if (L.kind == LINK_FIRST) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o0[t] = x0[t];
+                w0 = false;
+              } else {                             // hb = acc; zbar = hb * a + zz
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o0[t] = ac[t] * x0[t] + x2[t];
+              }
+            }
+            if (w0) st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+            if (want_lo) st4(b1 + off, make_float4(lo_part(o0[0]), lo_part(o0[1]), lo_part(o0[2]), lo_part(o0[3])));
+            if (w2) st4(b2 + off, make_float4(o2[0], o2[1], o2[2], o2[3]));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA / TMA store
+          if (L.colsum) {
+            // column sums over this group's 128 rows: warp q adds its 32 rows of column (c0 + lane); the partials of
+            // the four row quarters stay apart (fixed owner thread per address: plain read-modify-write in global)
+            named_bar(2 + grp, 128);
+            float s0 = 0.f, s2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int rr = q * 32 + r;
+              const int idx = rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3);
+              s0 += b0[idx];
+              if (L.colsum & 2) s2 += b2[idx];
+            }
+            float* dst = a.colacc + ((size_t)(blockIdx.x * kMaxLinks + i) * 2) * 1024 + q * 256 + c0 + lane;
+            if (L.colsum & 1) dst[0] = first_tile ? s0 : dst[0] + s0;
+            if (L.colsum & 2) dst[1024] = first_tile ? s2 : dst[1024] + s2;
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&a_ready[s]);
+        }
+        cc += (uint32_t)nch;
+        if (has_acc) {
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+          ++mmr;
+        }
+        if (SWEEP == SWEEP_F && L.kind == LINK_LAST) {   // output head: u = h_L . wout + bout
+          ypart[grp * 128 + rt] = yacc;
+          named_bar(1, 128 * G);
+          if (grp == 0 && valid) {
+            float y = ypart[rt];
+#pragma unroll
+            for (int gg = 1; gg < G; ++gg) y += ypart[gg * 128 + rt];
+            a.Y[row] = y + __ldg(a.bout);
+          }
+          named_bar(1, 128 * G);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// out[c] = sum over CTAs and row quarters of the chain kernels' column-sum partials (fixed order, double accumulation)
+struct ColFinJob {
+  int slot, which, width;
+  float* out;
+};
+struct ColFinJobs {
+  ColFinJob job[2 * kMaxLinks];
+  int njobs, nblk;
+};
+__global__ void chain_colsum_finish_kernel(const float* __restrict__ colacc, const ColFinJobs js) {
+  const ColFinJob& j = js.job[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= j.width) return;
+  double acc = 0.0;
+  for (int b = 0; b < js.nblk; ++b) {
+    const float* p = colacc + ((size_t)(b * kMaxLinks + j.slot) * 2 + j.which) * 1024 + c;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc += (double)p[q * 256];
+  }
+  j.out[c] = (float)acc;
+}
+
+template <int SWEEP, bool X3>
+inline cudaError_t launch_chain(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {
+  using C = Cfg<X3>;
+  auto kern = chain_kernel<SWEEP, X3>;
+  static unsigned long long attr_devs = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
+  if (!((attr_devs >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_devs |= 1ull << dev;
+  }
+  const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;
+  return tc::launch_pdl(kern, grid, C::NUM_THREADS, C::SMEM_BYTES, st, 1, m, a);
+}
+
+}  // namespace chain
+}  // namespace fbsnn

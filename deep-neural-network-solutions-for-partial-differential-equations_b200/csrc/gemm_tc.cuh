@@ -519,18 +519,62 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 // 2-D fp32 tensor map over X[outer x inner] (inner contiguous, leading dimension ld), 128-byte swizzle.
+// Encoded maps are cached per (base, shape, box): the row arrays live at fixed workspace addresses, so after the first
+// iteration a launch costs a table lookup instead of a driver call per operand (matters for the small-M steps).
+struct MapKey {
+  const void* base;
+  long long inner, outer, ld;
+  int box_inner, box_outer, mn;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+           box_outer == o.box_outer && mn == o.mn;
+  }
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+  bool used;
+};
+constexpr int kMapCacheSlots = 1024;   // open addressing; cleared when three quarters full
 inline bool make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_inner,
                      int box_outer, bool mn_major) {
+  static thread_local MapSlot* cache = nullptr;
+  static thread_local int used = 0;
+  if (!cache) cache = (MapSlot*)calloc(kMapCacheSlots, sizeof(MapSlot));
+  const MapKey key{base, inner, outer, ld, box_inner, box_outer, mn_major ? 1 : 0};
+  unsigned long long h = (unsigned long long)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+  h ^= (unsigned long long)inner * 0xC2B2AE3D27D4EB4Full + (unsigned long long)outer * 0x165667B19E3779F9ull +
+       (unsigned long long)ld * 0x27D4EB2F165667C5ull + (unsigned long long)(box_inner * 131 + box_outer * 7 + key.mn);
+  int idx = (int)((h >> 20) % kMapCacheSlots);
+  if (cache) {
+    for (int probe = 0; probe < kMapCacheSlots; ++probe, idx = (idx + 1) % kMapCacheSlots) {
+      if (!cache[idx].used) break;
+      if (cache[idx].key == key) {
+        *m = cache[idx].map;
+        return true;
+      }
+    }
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
-         CUDA_SUCCESS;
+  const bool ok = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (ok && cache) {
+    if (used >= kMapCacheSlots * 3 / 4) {
+      memset(cache, 0, kMapCacheSlots * sizeof(MapSlot));
+      used = 0;
+      idx = (int)((h >> 20) % kMapCacheSlots);
+    }
+    while (cache[idx].used) idx = (idx + 1) % kMapCacheSlots;
+    cache[idx].key = key, cache[idx].map = *m, cache[idx].used = true;
+    ++used;
+  }
+  return ok;
 }
 
 }  // namespace tc

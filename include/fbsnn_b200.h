@@ -76,6 +76,10 @@ typedef struct FbsnnAdam {
 
 const char* fbsnn_last_error(void);
 int fbsnn_version(void);
+/* Run-time switch of the kernel dispatch (tests, A/B measurements; no reference counterpart).  "chain": 0 = one launch
+ * per dense layer, 1 = layer-chained sweep kernels once the row tiles fill the chip (default), 2 = always when the
+ * network is eligible (FC, widths multiples of 32 in [64, 256], tensor-core precision).  Returns the previous value. */
+int fbsnn_set_option(const char* name, int value);
 /* Measurement hooks used by bench.py: number of kernels this library has launched since it was loaded; and
  * optional CUDA-event timing of every dense-layer launch (enable, run, synchronise, read).
  * out8 = {launches, ms, algorithmic FLOPs, tcgen05 launches, tcgen05 ms, tcgen05 FLOPs, algorithmic HBM bytes,
@@ -90,6 +94,12 @@ const char* fbsnn_dense_timing_entry(int i, double* out4);   /* one recorded lau
  * a_kc: A[m*lda + k] (1) | A[k*lda + m] (0);  b_kc: B[n*ldb + k] (1) | B[k*ldb + n] (0);  C[m*ldc + n]. */
 int fbsnn_debug_gemm(int a_kc, int b_kc, int use_tc, int M, int N, int K, const float* A, int lda, const float* B,
                      int ldb, float* C, int ldc, void* stream);
+
+/* Test hook (tests/test_chain_gpu.py): float offset and row width of a named per-row array inside the workspace
+ * ("xin","Y","zf","V","ybar", and per hidden layer "g","a","delta","szz","hd"), to compare what two dispatch variants
+ * leave behind. */
+int fbsnn_debug_ws_offset(const FbsnnSpec* spec, int64_t n_paths, int with_grad, const char* name, int layer,
+                          int64_t* offset_out, int* width_out);
 
 /* Bytes of device scratch needed for `n_paths` paths (rows = n_paths * (N+1)).  `with_grad` = 0 sizes for
  * forward/predict only. */

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(lib, sym), f"{sym} declared in include/fbsnn_b200.h but not exported"
     assert set(pde._lib.EXPORTS) == declared
-    assert lib.fbsnn_version() == 101
+    assert lib.fbsnn_version() == pde.spec.ABI_VERSION
 
 
 def test_peer_buffer_layout_without_gpu():

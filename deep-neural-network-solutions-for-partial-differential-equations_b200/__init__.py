@@ -6,6 +6,7 @@ or through the `dnnpde_b200` alias module at the repository root.
 """
 from . import _lib, parallel, spec
 from . import basket_pricer
+from .comparators import BasicOptionPriceCalculator, BasketOptionPriceCalculator
 from .drivers import PredictionGenerator, TrainingPhases
 from .fbsnn import FBSNN
 from .mc_pricer import (AnalyticalBlackScholes, BasketOption, BlackScholesModel, CorrelationMatrix,
@@ -19,5 +20,5 @@ build = _lib.build
 __all__ = ["FBSNN", "Sine", "Naisnet", "BlackScholesBarenblatt", "BasketCallOption", "BSPDETestCase",
            "CallOption1D", "CallOptionND", "HamiltonJacobiBellman", "HestonFBSNN", "u_exact", "hjb_u_exact", "basket_pricer", "CorrelationMatrix",
            "BlackScholesModel", "BasketOption", "MonteCarloPricer", "AnalyticalBlackScholes", "build",
-           "TrainingPhases", "PredictionGenerator",
+           "TrainingPhases", "PredictionGenerator", "BasketOptionPriceCalculator", "BasicOptionPriceCalculator",
            "parallel", "spec"]

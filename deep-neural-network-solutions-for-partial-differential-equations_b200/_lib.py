@@ -101,6 +101,11 @@ def _declare(lib):
     lib.fbsnn_loss_grad.restype = c.c_int
     lib.fbsnn_loss_grad.argtypes = [c.POINTER(S.FbsnnSpec), f32p, f32p, f32p, f32p, f32p, i64, i64, c.c_float,
                                     i64, u64, u64, f32p, vp, sz, f32p, f32p, f32p, f32p, vp]
+    lib.fbsnn_loss_grad_step.restype = c.c_int
+    lib.fbsnn_loss_grad_step.argtypes = [c.POINTER(S.FbsnnSpec), f32p, f32p, f32p, f32p, f32p, i64, i64, c.c_float,
+                                         i64, u64, f32p, vp, vp, sz, f32p, f32p, f32p, vp]
+    lib.fbsnn_track_min.restype = c.c_int
+    lib.fbsnn_track_min.argtypes = [f32p, f32p, vp, f32p, f32p, i64, f32p, f32p, i64, vp]
     lib.fbsnn_adam_step.restype = c.c_int
     lib.fbsnn_adam_step.argtypes = [c.POINTER(S.FbsnnAdam), f32p, f32p, f32p, f32p, i64, vp, vp]
     lib.fbsnn_peer_allreduce_adam.restype = c.c_int
@@ -124,15 +129,20 @@ def _declare(lib):
     lib.mc_basket_price_delta.argtypes = [c.POINTER(S.McSpec), f32p, f32p, f32p, u64, u64, u64, vp, vp, vp, vp]
     lib.mc_hjb_exact.restype = c.c_int
     lib.mc_hjb_exact.argtypes = [c.c_int32, c.c_int32, f32p, f32p, c.c_float, u64, u64, vp, vp, vp]
+    lib.mc_bs_comparator.restype = c.c_int
+    lib.mc_bs_comparator.argtypes = [c.c_int32, vp, vp, i64, c.c_int32, c.c_int32, c.c_double, c.c_double, c.c_double,
+                                     c.c_double, c.c_int32, vp, vp, vp]
+    lib.mc_normal_rate_probe.restype = c.c_int
+    lib.mc_normal_rate_probe.argtypes = [u64, u64, vp, c.POINTER(u64), vp]
     lib.mc_generate_paths.restype = c.c_int
     lib.mc_generate_paths.argtypes = [c.POINTER(S.McSpec), f32p, f32p, u64, u64, u64, f32p, vp]
 
 
 EXPORTS = ["fbsnn_last_error", "fbsnn_version", "fbsnn_set_option", "fbsnn_launch_count", "fbsnn_dense_timing",
            "fbsnn_dense_timing_read", "fbsnn_dense_timing_entry", "fbsnn_debug_gemm", "fbsnn_debug_ws_offset", "fbsnn_workspace_bytes", "fbsnn_fetch_minibatch", "fbsnn_net_u",
-           "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_adam_step", "fbsnn_peer_buffer_floats", "fbsnn_peer_wait",
+           "fbsnn_forward", "fbsnn_loss_grad", "fbsnn_loss_grad_step", "fbsnn_track_min", "fbsnn_adam_step", "fbsnn_peer_buffer_floats", "fbsnn_peer_wait",
            "fbsnn_peer_allreduce_adam", "fbsnn_train_step", "mc_scratch_bytes", "mc_launch_count",
-           "mc_basket_price", "mc_basket_price_delta", "mc_hjb_exact", "mc_generate_paths"]
+           "mc_basket_price", "mc_basket_price_delta", "mc_hjb_exact", "mc_bs_comparator", "mc_normal_rate_probe", "mc_generate_paths"]
 
 
 def load():

@@ -524,6 +524,22 @@ static bool chain_eligible(const FbsnnSpec* s, const Plan& p) {
   if (chain_mode() == 1 && p.rows < (long long)num_sms() * 128) return false;
   return true;
 }
+// CTA-pair form of the chained sweeps (chain2_kernel): 3xTF32, every MMA width a multiple of 64 (each CTA stages half of
+// the weight columns in 32-column boxes).  Option "chain_pair": 0 = single-CTA chain kernel only, 1 = pair when eligible.
+static int g_opt_chain_pair = -1;
+static int chain_pair_mode() {
+  if (g_opt_chain_pair < 0) {
+    const char* e = getenv("FBSNN_CHAIN_PAIR");
+    g_opt_chain_pair = (e && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : 1;
+  }
+  return g_opt_chain_pair;
+}
+static bool chain_use_pair(const Plan& p) {
+  if (!p.x3 || chain_pair_mode() == 0 || p.ldx % 64) return false;
+  for (int l = 1; l <= p.L; ++l)
+    if (p.H[l] % 64) return false;
+  return true;
+}
 static bool row_map(CUtensorMap* m, const float* base, int width, long long rows) {
   return tc::make_map(m, base, width, rows, width, 32, 128, false);
 }
@@ -533,9 +549,10 @@ static bool weight_maps(const Plan& p, const Net& n, float* ws, int l, bool b_mn
   const int Hl = p.H[l];
   const float* hi = p.x3 ? ws + p.Whi[l] : n.W[l];
   const float* lo = p.x3 ? ws + p.Wlo[l] : n.W[l];
+  const int box_n = chain_use_pair(p) ? Hl / 2 : Hl;   // pair: each CTA loads half of the N rows of W^T
   bool ok;
   if (!b_mn) {   // out = A[rows x K] * W^T: B[n = H_l][k]
-    ok = tc::make_map(&m.whi[i], hi, K, Hl, K, 32, Hl, false) && tc::make_map(&m.wlo[i], lo, K, Hl, K, 32, Hl, false);
+    ok = tc::make_map(&m.whi[i], hi, K, Hl, K, 32, box_n, false) && tc::make_map(&m.wlo[i], lo, K, Hl, K, 32, box_n, false);
   } else {       // out = A[rows x H_l] * W: B[k = H_l][n = K]
     ok = tc::make_map(&m.whi[i], hi, K, Hl, K, 32, 32, true) && tc::make_map(&m.wlo[i], lo, K, Hl, K, 32, 32, true);
   }
@@ -559,12 +576,19 @@ static void chain_timing_begin(int& slot, const chain::Args& a, const char* what
   cudaEventRecord(g_ev0[slot], st);
 }
 template <int SWEEP>
-static int chain_launch(const FbsnnSpec* s, const chain::Maps& m, const chain::Args& a, const char* what, cudaStream_t st) {
+static int chain_launch(const FbsnnSpec* s, const Plan& p, const chain::Maps& m, chain::Args& a, const char* what,
+                        cudaStream_t st) {
   int slot;
   chain_timing_begin(slot, a, what, st);
   ++g_launches;
-  const cudaError_t e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chain<SWEEP, true>(m, a, num_sms(), st)
-                                                           : chain::launch_chain<SWEEP, false>(m, a, num_sms(), st);
+  cudaError_t e;
+  if (chain_use_pair(p)) {
+    a.ntiles = (int)((p.rows + 255) / 256);   // 256-row tiles, one per CTA pair
+    e = chain::launch_chain2<SWEEP>(m, a, num_sms(), st);
+  } else {
+    e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chain<SWEEP, true>(m, a, num_sms(), st)
+                                          : chain::launch_chain<SWEEP, false>(m, a, num_sms(), st);
+  }
   if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
   if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "chained sweep %s: %s", what, cudaGetErrorString(e));
   static int debug = -1;
@@ -616,7 +640,7 @@ static int chain_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float*
       if (!last) ok = ok && weight_maps(p, n, ws, l + 1, false, m, l);
     }
     if (!ok) return fail(FBSNN_E_CUDA, "chained F sweep: tensor map encoding failed");
-    int rc = chain_launch<chain::SWEEP_F>(s, m, a, "F*", st);
+    int rc = chain_launch<chain::SWEEP_F>(s, p, m, a, "F*", st);
     if (rc) return rc;
   }
   {
@@ -640,7 +664,7 @@ static int chain_forward(const FbsnnSpec* s, const Plan& p, const Net& n, float*
     a.link[L] = chain::LinkD{p.ldx, 0, chain::LINK_LAST, 0, 0, 1, 0, 0, 0, 0};
     ok = ok && row_map(&m.out0[L], ws + p.zf, p.ldx, R);
     if (!ok) return fail(FBSNN_E_CUDA, "chained A sweep: tensor map encoding failed");
-    int rc = chain_launch<chain::SWEEP_A>(s, m, a, "A*", st);
+    int rc = chain_launch<chain::SWEEP_A>(s, p, m, a, "A*", st);
     if (rc) return rc;
   }
   return 0;
@@ -671,11 +695,11 @@ static int chain_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     ok = ok && row_map(&m.in0[L], ws + p.a[L], p.H[L], R) && row_map(&m.in2[L], ws + p.g[L], p.H[L], R) &&
          row_map(&m.out0[L], ws + p.szz[L], p.H[L], R);
     if (!ok) return fail(FBSNN_E_CUDA, "chained T sweep: tensor map encoding failed");
-    int rc = chain_launch<chain::SWEEP_T>(s, m, a, "T*", st);
+    int rc = chain_launch<chain::SWEEP_T>(s, p, m, a, "T*", st);
     if (rc) return rc;
     fin.job[fin.njobs++] = chain::ColFinJob{L, 0, p.H[L], grads + s->off_b[L]};
     fin.job[fin.njobs++] = chain::ColFinJob{L, 1, p.H[L], grads + s->off_W[L + 1]};
-    fin.nblk = std::min(a.ntiles, num_sms());
+    fin.nblk = chain_use_pair(p) ? chain::chain2_grid((int)((p.rows + 255) / 256), num_sms()) : std::min(a.ntiles, num_sms());
   }
   if (L >= 2) {
     chain::Maps m;
@@ -696,7 +720,7 @@ static int chain_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float
       fin.job[fin.njobs++] = chain::ColFinJob{k, 0, p.H[l], grads + s->off_b[l]};
     }
     if (!ok) return fail(FBSNN_E_CUDA, "chained B sweep: tensor map encoding failed");
-    int rc = chain_launch<chain::SWEEP_B>(s, m, a, "B*", st);
+    int rc = chain_launch<chain::SWEEP_B>(s, p, m, a, "B*", st);
     if (rc) return rc;
   }
   chain::chain_colsum_finish_kernel<<<dim3(1, fin.njobs), 256, 0, st>>>(colacc, fin);
@@ -1063,7 +1087,7 @@ using namespace fbsnn;
 extern "C" {
 
 const char* fbsnn_last_error(void) { return g_err; }
-int fbsnn_version(void) { return 102; }
+int fbsnn_version(void) { return 103; }
 // Run-time switches (tests and A/B measurements): "chain" = 0 | 1 | 2 (layer-chained sweeps: off / auto / always when
 // eligible).  Returns the previous value, or FBSNN_E_BADARG for an unknown name.
 int fbsnn_set_option(const char* name, int value) {
@@ -1071,6 +1095,12 @@ int fbsnn_set_option(const char* name, int value) {
     const int old = chain_mode();
     if (value < 0 || value > 2) return fail(FBSNN_E_BADARG, "option chain takes 0, 1 or 2");
     g_opt_chain = value;
+    return old;
+  }
+  if (name && !strcmp(name, "chain_pair")) {
+    const int old = chain_pair_mode();
+    if (value < 0 || value > 1) return fail(FBSNN_E_BADARG, "option chain_pair takes 0 or 1");
+    g_opt_chain_pair = value;
     return old;
   }
   return fail(FBSNN_E_BADARG, "unknown option %s", name ? name : "(null)");
@@ -1269,6 +1299,35 @@ int fbsnn_loss_grad(const FbsnnSpec* spec, const float* params, float* grads, co
                     void* stream) {
   return loss_grad_impl(spec, params, grads, t, W, Xi, xi_rows, n_paths, T, path_offset, seed, iteration, nullptr,
                         chol, workspace, workspace_bytes, X_out, Y_out, Z_out, loss_out, true, (cudaStream_t)stream);
+}
+
+int fbsnn_loss_grad_step(const FbsnnSpec* spec, const float* params, float* grads, const float* t, const float* W,
+                         const float* Xi, int64_t xi_rows, int64_t n_paths, float T, int64_t path_offset,
+                         uint64_t seed, const float* chol, const void* opt_state, void* workspace,
+                         size_t workspace_bytes, float* X_out, float* Y_out, float* loss_out, void* stream) {
+  if (!opt_state) return fail(FBSNN_E_BADARG, "opt_state is null");
+  return loss_grad_impl(spec, params, grads, t, W, Xi, xi_rows, n_paths, T, path_offset, seed, 0,
+                        &((const OptState*)opt_state)->rng_iter, chol, workspace, workspace_bytes, X_out, Y_out, nullptr,
+                        loss_out, true, (cudaStream_t)stream);
+}
+
+int fbsnn_track_min(const float* loss, float* state, const void* opt_state, const float* X, float* X_best, int64_t n_x,
+                    const float* Y, float* Y_best, int64_t n_y, void* stream) {
+  if (!loss || !state || n_x < 0 || n_y < 0 || n_x % 4 || n_y % 4 || (n_x && (!X || !X_best)) || (n_y && (!Y || !Y_best)))
+    return fail(FBSNN_E_BADARG, "track_min: null pointer or element counts that are not multiples of 4");
+  if ((((uintptr_t)X | (uintptr_t)X_best | (uintptr_t)Y | (uintptr_t)Y_best) & 15) != 0)
+    return fail(FBSNN_E_BADARG, "track_min: arrays must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  track_min_decide_kernel<<<1, 1, 0, st>>>(loss, state, (const OptState*)opt_state);
+  LAUNCH_CHECK("track_min_decide");
+  const long long n4 = (n_x + n_y) / 4;
+  if (n4 > 0) {
+    const unsigned blocks = (unsigned)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
+    track_min_copy_kernel<<<blocks, 256, 0, st>>>(state, (const float4*)X, (float4*)X_best, n_x / 4, (const float4*)Y,
+                                                  (float4*)Y_best, n_y / 4);
+    LAUNCH_CHECK("track_min_copy");
+  }
+  return 0;
 }
 
 int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads, float* exp_avg,

@@ -19,8 +19,18 @@
 // Warps: 0 weight producer | 1 MMA issuer (owns TMEM) | 2 input producer | 3 store | 4.. epilogue groups.
 // Shared memory (3xTF32): 2 weight stages x (W_hi 32 KB + W_lo 32 KB) + 2 A stages x 3 x 16 KB = 224 KB;
 // (TF32): 4 weight stages x 32 KB + 3 A stages x 2 x 16 KB = 224 KB.
+//
+// chain2_kernel is the CTA-PAIR form (cluster of 2, tcgen05.mma.cta_group::2, 256-row tiles) for 3xTF32: each CTA
+// stages its own 128 rows of every chunk and only HALF of every weight k-block (the pair's MMA reads both halves), which
+// (i) halves the weight traffic through L2 -- measured to be what bounds the sweeps: every 128-row tile re-fetches the
+// 512 KB hi/lo weight twins of every layer -- and (ii) frees 64 KB of shared memory for a THIRD A stage, so that input
+// load, epilogue, MMA and store of consecutive chunks overlap instead of queueing on two buffers (ablation timings in
+// profiles/r02_chain_ablation.txt).  Cross-CTA signalling: the peer's TMA completes on the LEADER's weight barrier, one
+// elected thread per chunk arrives on the leader's a_ready, the leader's tcgen05.commit multicasts to both CTAs.
 #pragma once
-#include "gemm_tc.cuh"
+#include <cstdio>
+
+#include "gemm_tc2.cuh"
 
 namespace fbsnn {
 namespace chain {
@@ -59,9 +69,15 @@ struct Cfg {
   static constexpr int A_BUFS = X3 ? 3 : 2;                  // [buf0][buf1 = lo (3xTF32 only)][buf2]
   static constexpr int A_STAGE = A_BUFS * CHUNK_BYTES;
   static constexpr int A_STAGES = X3 ? 2 : 3;
-  static constexpr int GROUPS = A_STAGES;                    // epilogue groups of 4 warps
+  // ONE epilogue team works on ONE chunk at a time, its 16 warps splitting the chunk's 32 columns (lane quarter q = warp
+  // % 4 owns 32 rows, column slice h = warp / 4 owns 8 columns), and the chunks alternate between the A stages: the
+  // epilogue of chunk c+1 then overlaps the MMAs and the TMA store of chunk c.  (Two independent 4-warp groups, one per
+  // stage, measured 2x slower: a group's next chunk reuses the stage of its previous one and so waits out that chunk's
+  // MMA + store + re-load round trip of ~3 us every time -- profiles/r02_chain_ablation.txt.)
+  static constexpr int EPI_WARPS = 16;
+  static constexpr int CW = 32 / (EPI_WARPS / 4);            // columns per epilogue warp
   static constexpr int EPI_WARP0 = 4;
-  static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + 4 * GROUPS);
+  static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
   static constexpr int B2_OFF = (A_BUFS - 1) * CHUNK_BYTES;  // byte offset of buf2 inside a stage
   static constexpr int EXTRA_BYTES = 2048;                   // barriers, TMEM slot, head partials
   static constexpr int SMEM_BYTES = W_STAGES * W_STAGE + A_STAGES * A_STAGE + EXTRA_BYTES + 1024 /*align*/;
@@ -94,13 +110,160 @@ __device__ __forceinline__ void cwait(uint64_t* b, uint32_t parity, int role, in
     if (++spins > tc::kSpinLimit) chain_timeout(role, what, link, chunk);
   }
 }
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) {
+  if constexpr (CW == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+  } else if constexpr (CW == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+  } else {
+    static_assert(CW == 32, "column slice of 8, 16 or 32");
+    FBSNN_TMEM_LD32(taddr, v);
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float lo_part(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// ----------------------------------------------------------------------------------------------------------------
+// shared pieces of the single-CTA and the CTA-pair kernel
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+// position in the chunk sequence (tile, link, chunk) of one CTA; `step` = tiles between consecutive tiles of this CTA
+struct ChunkIt {
+  int tile, link, j;
+  __device__ __forceinline__ bool valid(const Args& a) const { return tile < a.ntiles; }
+  __device__ __forceinline__ void next(const Args& a, int step) {
+    if (++j >= (a.link[link].width >> 5)) {
+      j = 0;
+      if (++link >= a.nlinks) link = 0, tile += step;
+    }
+  }
+};
+
+// One 32-column chunk of link `i` for the thread that owns row `rt` of the tile: combines the accumulator fragment v[]
+// with the loaded chunks (buf0 / buf2) and writes the results back in place (buf0, its low part buf1, buf2).
+// CW = columns of the chunk this thread handles, starting at column u0 * 4 of the chunk (v[] = its accumulator fragment).
+// (i0, i2) = where the loaded input chunks are: the output buffers themselves (in-place, single-CTA kernel) or a separate
+// input ring (CTA-pair kernel; pass-through links then have to copy their operand into buf0).
+template <int SWEEP, bool X3, int CW, bool INPLACE>
+__device__ __forceinline__ void chunk_math(const Args& a, const LinkD& L, int i, int c0, int rt, int u0, const float* i0,
+                                           const float* i2, float* b0, float* b1, float* b2, const uint32_t (&v)[CW],
+                                           float yb, float& yacc) {
+  const int rsw = rt & 7;
+  const bool want_lo = X3 && L.feeds;
+#pragma unroll
+  for (int uu = 0; uu < CW / 4; ++uu) {
+    const int u = u0 + uu;
+    const int off = rt * 32 + ((u ^ rsw) << 2);
+    float x0[4] = {0.f, 0.f, 0.f, 0.f}, x2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (L.in0) { const float4 t = ld4(i0 + off); x0[0] = t.x, x0[1] = t.y, x0[2] = t.z, x0[3] = t.w; }
+    if (L.in2) { const float4 t = ld4(i2 + off); x2[0] = t.x, x2[1] = t.y, x2[2] = t.z, x2[3] = t.w; }
+    const float ac[4] = {__uint_as_float(v[4 * uu]), __uint_as_float(v[4 * uu + 1]), __uint_as_float(v[4 * uu + 2]),
+                         __uint_as_float(v[4 * uu + 3])};
+    float o0[4], o2[4];
+    bool w0 = true, w2 = false;
+    if constexpr (SWEEP == SWEEP_F) {
+      if (L.kind == LINK_FIRST) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = x0[t];
+        w0 = !INPLACE;
+      } else {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias[i] + c0 + 4 * u));
+        const float z[4] = {ac[0] + b.x, ac[1] + b.y, ac[2] + b.z, ac[3] + b.w};
+        act_ga4(a.act, z, o0, o2);
+        w2 = true;
+        if (L.kind == LINK_LAST) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
+          yacc = fmaf(o0[0], w.x, fmaf(o0[1], w.y, fmaf(o0[2], w.z, fmaf(o0[3], w.w, yacc))));
+        }
+      }
+    } else if constexpr (SWEEP == SWEEP_A) {
+      if (L.kind == LINK_FIRST) {          // delta_L = wout * a_L
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
+        o0[0] = w.x * x0[0], o0[1] = w.y * x0[1], o0[2] = w.z * x0[2], o0[3] = w.w * x0[3];
+      } else if (L.kind == LINK_MID) {     // ht = acc; delta = ht * a; s = ht * c(g, a)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          o0[t] = ac[t] * x0[t];
+          o2[t] = ac[t] * act_c(a.act, x2[t], x0[t]);
+        }
+        w2 = a.with_s != 0;
+      } else {                             // Du
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = ac[t];
+      }
+    } else if constexpr (SWEEP == SWEEP_T) {
+      if (L.kind == LINK_FIRST) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = x0[t];
+        w0 = !INPLACE;
+      } else if (L.kind == LINK_MID) {     // dbar = acc; hd = dbar * a; zz = dbar * s
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = ac[t] * x0[t], o2[t] = ac[t] * x2[t];
+        w2 = true;
+      } else {   // last hidden layer: zbar = ybar wout a + dbar (wout c);  wg = dbar a + ybar g  (column sums only)
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float av = x0[t], gv = x2[t];
+          const float sv = w[t] * act_c(a.act, gv, av);
+          const float zz = ac[t] * sv;
+          o0[t] = zz + yb * w[t] * av;
+          o2[t] = ac[t] * av + yb * gv;
+        }
+        w2 = true;
+      }
+    } else {
+      if (L.kind == LINK_FIRST) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = x0[t];
+        w0 = !INPLACE;
+      } else {                             // hb = acc; zbar = hb * a + zz
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = ac[t] * x0[t] + x2[t];
+      }
+    }
+    if (w0) st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+    if (want_lo) st4(b1 + off, make_float4(lo_part(o0[0]), lo_part(o0[1]), lo_part(o0[2]), lo_part(o0[3])));
+    if (w2) st4(b2 + off, make_float4(o2[0], o2[1], o2[2], o2[3]));
+  }
+}
+
+// column sums over a group's 128 rows of the chunk in buf0 (/ buf2): warp q adds its 32 rows of column (c0 + lane); the
+// partials of the four row quarters stay apart -- every address has ONE owner thread for the whole launch (chunk j of a
+// link always goes to group j % G), so the accumulation is a plain, ordered read-modify-write in global memory
+__device__ __forceinline__ void chunk_colsum(const Args& a, const LinkD& L, int i, int c0, int q, int lane,
+                                             const float* b0, const float* b2, bool first_tile) {
+  float s0 = 0.f, s2 = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const int rr = q * 32 + r;
+    const int idx = rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3);
+    s0 += b0[idx];
+    if (L.colsum & 2) s2 += b2[idx];
+  }
+  float* dst = a.colacc + ((size_t)(blockIdx.x * kMaxLinks + i) * 2) * 1024 + q * 256 + c0 + lane;
+  if (L.colsum & 1) dst[0] = first_tile ? s0 : dst[0] + s0;
+  if (L.colsum & 2) dst[1024] = first_tile ? s2 : dst[1024] + s2;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// single-CTA kernel
+// ----------------------------------------------------------------------------------------------------------------
 template <int SWEEP, bool X3>
 __global__ void __launch_bounds__(Cfg<X3>::NUM_THREADS, 1)
 chain_kernel(const __grid_constant__ Maps tm, const Args a) {
   using C = Cfg<X3>;
-  constexpr int AS = C::A_STAGES, WS = C::W_STAGES, G = C::GROUPS;
+  constexpr int AS = C::A_STAGES, WS = C::W_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* wring = smem;
@@ -110,12 +273,13 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
   uint64_t* w_full = bars;           // [WS]  weight k-block landed
   uint64_t* w_empty = bars + 4;      // [WS]  MMAs that read it completed
   uint64_t* in_full = bars + 8;      // [AS]  input chunks landed (or: stage handed to the epilogue)
-  uint64_t* a_ready = bars + 12;     // [AS]  epilogue group has written the chunk (4 warp arrivals)
+  uint64_t* a_ready = bars + 12;     // [AS]  the epilogue team has written the chunk (one arrival per warp)
   uint64_t* a_free = bars + 16;      // [AS]  MMAs that read the chunk completed + TMA stores have read it
   uint64_t* acc_full = bars + 20;    // [2]
   uint64_t* acc_empty = bars + 22;   // [2]   all epilogue warps have drained the accumulator
   uint32_t* tmem_slot = (uint32_t*)(bars + 24);
-  float* ypart = (float*)(extra + 256);   // [G][128] head partial sums (F sweep)
+  float* ypart = (float*)(extra + 256);   // [EPI_WARPS / 4 - 1][128] head partial sums (F sweep)
+  constexpr int EW = C::EPI_WARPS, CW = C::CW;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -132,8 +296,8 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
       }
     }
     for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
-    for (int i = 0; i < AS; ++i) tc::mbar_init(&in_full[i], 1), tc::mbar_init(&a_ready[i], 4), tc::mbar_init(&a_free[i], 2);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], 4 * G);
+    for (int i = 0; i < AS; ++i) tc::mbar_init(&in_full[i], 1), tc::mbar_init(&a_ready[i], EW), tc::mbar_init(&a_free[i], 2);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -183,6 +347,17 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     // ===================== input producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      // the row arrays of the chunks a few positions ahead are pulled into L2 now, so that the TMA load issued when the
+      // stage frees up pays an L2 hit instead of the HBM latency (that latency sits inside the stage's occupancy)
+      ChunkIt pf{(int)blockIdx.x, 0, 0};
+      auto prefetch_one = [&]() {
+        if (!pf.valid(a) || (a.ablate & 2)) return;
+        const LinkD& P = a.link[pf.link];
+        if (P.in0) tma_prefetch_2d(&tm.in0[pf.link], 32 * pf.j, pf.tile * 128);
+        if (P.in2) tma_prefetch_2d(&tm.in2[pf.link], 32 * pf.j, pf.tile * 128);
+        pf.next(a, (int)gridDim.x);
+      };
+      for (int p = 0; p < AS + 2; ++p) prefetch_one();
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int m0 = tile * 128;
         for (int i = 0; i < a.nlinks; ++i) {
@@ -190,13 +365,15 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
           const int nch = L.width >> 5;
           for (int j = 0; j < nch; ++j) {
             cwait(&a_free[s], ph ^ 1, 2, 0, i, j);
+            prefetch_one();
             uint8_t* st = aring + s * C::A_STAGE;
+            uint64_t* bar = &in_full[s];
             if ((L.in0 || L.in2) && !(a.ablate & 2)) {
-              tc::mbar_expect_tx(&in_full[s], (uint32_t)CHUNK_BYTES * (uint32_t)((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0)));
-              if (L.in0) tc::tma_load_2d(st, &tm.in0[i], &in_full[s], 32 * j, m0);
-              if (L.in2) tc::tma_load_2d(st + C::B2_OFF, &tm.in2[i], &in_full[s], 32 * j, m0);
+              tc::mbar_expect_tx(bar, (uint32_t)CHUNK_BYTES * (uint32_t)((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0)));
+              if (L.in0) tc::tma_load_2d(st, &tm.in0[i], bar, 32 * j, m0);
+              if (L.in2) tc::tma_load_2d(st + C::B2_OFF, &tm.in2[i], bar, 32 * j, m0);
             } else {
-              tc::mbar_arrive(&in_full[s]);
+              tc::mbar_arrive(bar);
             }
             if (++s == AS) s = 0, ph ^= 1;
           }
@@ -225,24 +402,24 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
               cwait(&w_full[ws], wph, 1, 2, i, j);
               tc::tc_fence_after();
               if (!(a.ablate & 8)) {
-              const uint32_t a0 = smem_u32(aring + s * C::A_STAGE);
-              const uint32_t alo = a0 + CHUNK_BYTES;
-              const uint32_t b0 = smem_u32(wring + ws * C::W_STAGE);
-              const uint32_t blo = b0 + 32768;
+                const uint32_t a0 = smem_u32(aring + s * C::A_STAGE);
+                const uint32_t alo = a0 + CHUNK_BYTES;
+                const uint32_t b0 = smem_u32(wring + ws * C::W_STAGE);
+                const uint32_t blo = b0 + 32768;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = tc::make_desc(a0 + k * 32, 16, 1024, 2);
-                const uint64_t db = L.b_mn ? tc::make_desc(b0 + k * 1024, 4096, 512, 1) : tc::make_desc(b0 + k * 32, 16, 1024, 2);
-                if (X3) {
-                  const uint64_t dal = tc::make_desc(alo + k * 32, 16, 1024, 2);
-                  const uint64_t dbl = L.b_mn ? tc::make_desc(blo + k * 1024, 4096, 512, 1) : tc::make_desc(blo + k * 32, 16, 1024, 2);
-                  tc::umma_tf32(tmem_d, dal, db, idesc, (j | k) ? 1u : 0u);
-                  tc::umma_tf32(tmem_d, da, dbl, idesc, 1u);
-                  tc::umma_tf32(tmem_d, da, db, idesc, 1u);
-                } else {
-                  tc::umma_tf32(tmem_d, da, db, idesc, (j | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da = tc::make_desc(a0 + k * 32, 16, 1024, 2);
+                  const uint64_t db = L.b_mn ? tc::make_desc(b0 + k * 1024, 4096, 512, 1) : tc::make_desc(b0 + k * 32, 16, 1024, 2);
+                  if (X3) {
+                    const uint64_t dal = tc::make_desc(alo + k * 32, 16, 1024, 2);
+                    const uint64_t dbl = L.b_mn ? tc::make_desc(blo + k * 1024, 4096, 512, 1) : tc::make_desc(blo + k * 32, 16, 1024, 2);
+                    tc::umma_tf32(tmem_d, dal, db, idesc, (j | k) ? 1u : 0u);
+                    tc::umma_tf32(tmem_d, da, dbl, idesc, 1u);
+                    tc::umma_tf32(tmem_d, da, db, idesc, 1u);
+                  } else {
+                    tc::umma_tf32(tmem_d, da, db, idesc, (j | k) ? 1u : 0u);
+                  }
                 }
-              }
               }
               tc::umma_commit(&w_empty[ws]);
               if (++ws == WS) ws = 0, wph ^= 1;
@@ -284,13 +461,12 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
     }
   } else {
-    // ===================== epilogue groups =====================
+    // ===================== epilogue team: one chunk at a time, 16 warps = 4 row quarters x 4 column slices ==========
     const int e = warp - C::EPI_WARP0;
-    const int q = warp & 3;          // TMEM lane quarter
-    const int grp = e >> 2;
+    const int q = warp & 3;          // TMEM lane quarter (rows 32q .. 32q+31 of the tile)
+    const int h = e >> 2;            // column slice: columns [h * CW, (h + 1) * CW) of every chunk
     const int rt = q * 32 + lane;    // row inside the tile
-    const int rsw = rt & 7;
-    uint32_t cc = 0, mmr = 0;
+    uint32_t s = 0, ph = 0, mmr = 0;
     bool first_tile = true;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, first_tile = false) {
       const int row = tile * 128 + rt;
@@ -307,119 +483,26 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
           tc::tc_fence_after();
         }
         for (int j = 0; j < nch; ++j) {
-          if (j % G != grp) continue;
-          const uint32_t cj = cc + (uint32_t)j;
-          const uint32_t s = cj % AS, ph = (cj / AS) & 1;
           cwait(&in_full[s], ph, 4, 1, i, j);
           float* b0 = (float*)(aring + s * C::A_STAGE);
           float* b1 = b0 + CHUNK_BYTES / 4;
           float* b2 = (float*)(aring + s * C::A_STAGE + C::B2_OFF);
-          uint32_t v[32];
+          uint32_t v[CW];
           if (has_acc) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (uint32_t)(32 * j);
-            FBSNN_TMEM_LD32(taddr, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (uint32_t)(32 * j + h * CW);
+            tmem_ld_cols<CW>(taddr, v);
           }
           const int c0 = 32 * j;
-          const bool want_lo = X3 && L.feeds;
-          if (!(a.ablate & 4))
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int off = rt * 32 + ((u ^ rsw) << 2);
-            float x0[4] = {0.f, 0.f, 0.f, 0.f}, x2[4] = {0.f, 0.f, 0.f, 0.f};
-            if (L.in0) { const float4 t = ld4(b0 + off); x0[0] = t.x, x0[1] = t.y, x0[2] = t.z, x0[3] = t.w; }
-            if (L.in2) { const float4 t = ld4(b2 + off); x2[0] = t.x, x2[1] = t.y, x2[2] = t.z, x2[3] = t.w; }
-            const float ac[4] = {__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
-                                 __uint_as_float(v[4 * u + 3])};
-            float o0[4], o2[4];
-            bool w0 = true, w2 = false;
-            if constexpr (SWEEP == SWEEP_F) {
-              if (L.kind == LINK_FIRST) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o0[t] = x0[t];
-                w0 = false;
-              } else {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias[i] + c0 + 4 * u));
-                const float z[4] = {ac[0] + b.x, ac[1] + b.y, ac[2] + b.z, ac[3] + b.w};
-                act_ga4(a.act, z, o0, o2);
-                w2 = true;
-                if (L.kind == LINK_LAST) {
-                  const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
-                  yacc = fmaf(o0[0], w.x, fmaf(o0[1], w.y, fmaf(o0[2], w.z, fmaf(o0[3], w.w, yacc))));
-                }
-              }
-            } else if constexpr (SWEEP == SWEEP_A) {
-              if (L.kind == LINK_FIRST) {          // delta_L = wout * a_L
-                const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
-                o0[0] = w.x * x0[0], o0[1] = w.y * x0[1], o0[2] = w.z * x0[2], o0[3] = w.w * x0[3];
-              } else if (L.kind == LINK_MID) {     // ht = acc; delta = ht * a; s = ht * c(g, a)
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  o0[t] = ac[t] * x0[t];
-                  o2[t] = ac[t] * act_c(a.act, x2[t], x0[t]);
-                }
-                w2 = a.with_s != 0;
-              } else {                             // Du
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o0[t] = ac[t];
-              }
-            } else if constexpr (SWEEP == SWEEP_T) {
-              if (L.kind == LINK_FIRST) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o0[t] = x0[t];
-                w0 = false;
-              } else if (L.kind == LINK_MID) {     // dbar = acc; hd = dbar * a; zz = dbar * s
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o0[t] = ac[t] * x0[t], o2[t] = ac[t] * x2[t];
-                w2 = true;
-              } else {   // last hidden layer: zbar = ybar wout a + dbar (wout c);  wg = dbar a + ybar g  (column sums only)
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wout + c0 + 4 * u));
-                const float w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const float av = x0[t], gv = x2[t];
-                  const float sv = w[t] * act_c(a.act, gv, av);
-                  const float zz = ac[t] * sv;
-                  o0[t] = zz + yb * w[t] * av;
-                  o2[t] = ac[t] * av + yb * gv;
-                }
-                w2 = true;
-              }
-            } else {
-              if (L.kind == LINK_FIRST) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o0[t] = x0[t];
-                w0 = false;
-              } else {                             // hb = acc; zbar = hb * a + zz
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o0[t] = ac[t] * x0[t] + x2[t];
-              }
-            }
-            if (w0) st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
-            if (want_lo) st4(b1 + off, make_float4(lo_part(o0[0]), lo_part(o0[1]), lo_part(o0[2]), lo_part(o0[3])));
-            if (w2) st4(b2 + off, make_float4(o2[0], o2[1], o2[2], o2[3]));
-          }
+          if (!(a.ablate & 4)) chunk_math<SWEEP, X3, CW, true>(a, L, i, c0, rt, h * (CW / 4), b0, b2, b0, b1, b2, v, yb, yacc);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA / TMA store
           if (L.colsum) {
-            // column sums over this group's 128 rows: warp q adds its 32 rows of column (c0 + lane); the partials of
-            // the four row quarters stay apart (fixed owner thread per address: plain read-modify-write in global)
-            named_bar(2 + grp, 128);
-            float s0 = 0.f, s2 = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const int rr = q * 32 + r;
-              const int idx = rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3);
-              s0 += b0[idx];
-              if (L.colsum & 2) s2 += b2[idx];
-            }
-            float* dst = a.colacc + ((size_t)(blockIdx.x * kMaxLinks + i) * 2) * 1024 + q * 256 + c0 + lane;
-            if (L.colsum & 1) dst[0] = first_tile ? s0 : dst[0] + s0;
-            if (L.colsum & 2) dst[1024] = first_tile ? s2 : dst[1024] + s2;
+            named_bar(1, 32 * EW);                                       // the whole chunk is written
+            if (h == 0) chunk_colsum(a, L, i, c0, q, lane, b0, b2, first_tile);
           }
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&a_ready[s]);
+          if (++s == AS) s = 0, ph ^= 1;
         }
-        cc += (uint32_t)nch;
         if (has_acc) {
           tc::tc_fence_before();
           __syncwarp();
@@ -427,15 +510,15 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
           ++mmr;
         }
         if (SWEEP == SWEEP_F && L.kind == LINK_LAST) {   // output head: u = h_L . wout + bout
-          ypart[grp * 128 + rt] = yacc;
-          named_bar(1, 128 * G);
-          if (grp == 0 && valid) {
-            float y = ypart[rt];
+          if (h > 0) ypart[(h - 1) * 128 + rt] = yacc;
+          named_bar(1, 32 * EW);
+          if (h == 0 && valid) {
+            float y = yacc;
 #pragma unroll
-            for (int gg = 1; gg < G; ++gg) y += ypart[gg * 128 + rt];
+            for (int hh = 1; hh < EW / 4; ++hh) y += ypart[(hh - 1) * 128 + rt];
             a.Y[row] = y + __ldg(a.bout);
           }
-          named_bar(1, 128 * G);
+          named_bar(1, 32 * EW);
         }
       }
     }
@@ -445,6 +528,323 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
   if (warp == 1) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel (3xTF32): cluster (2,1,1), tile = 256 rows (128 per CTA), tcgen05.mma.cta_group::2 issued by the
+// leader (cluster rank 0).  Staging only half of every weight k-block per CTA frees the shared memory for what the
+// single-CTA kernel lacks: an INPUT ring separate from the output ring, so that the row-array chunks of the next chunks
+// are already on chip when the epilogue gets to them (in the single-CTA kernel a chunk's inputs land in the very buffers
+// the previous use of the stage is still being read from by the MMA and the TMA store, which puts the whole load latency
+// on the critical path: removing either the loads or the stores there takes 13.4 -> 8.7 ms off the A sweep).
+// Per CTA: weights 2 x (W_hi half 16 KB + W_lo half 16 KB) | out ring 2 x (buf0, lo, buf2 = 48 KB) | in ring 2 x (in0,
+// in2 = 32 KB) = 224 KB.  One epilogue team of 16 warps per CTA (4 row quarters x 4 column slices) works on one chunk at a
+// time; the chunks alternate between the two out-ring stages, so its work overlaps the MMAs / stores of the chunk before.
+// ----------------------------------------------------------------------------------------------------------------
+struct Cfg2 {
+  static constexpr int W_STAGE = 32768, W_STAGES = 2;
+  static constexpr int O_STAGE = 3 * CHUNK_BYTES, O_STAGES = 2;
+  static constexpr int I_STAGE = 2 * CHUNK_BYTES, I_STAGES = 2;
+  static constexpr int EPI_WARPS = 16, CW = 32 / (EPI_WARPS / 4);
+  static constexpr int EPI_WARP0 = 4;
+  static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+  static constexpr int B2_OFF = 2 * CHUNK_BYTES;
+  static constexpr int SMEM_BYTES = W_STAGES * W_STAGE + O_STAGES * O_STAGE + I_STAGES * I_STAGE + 2048 + 1024;
+};
+// TMA load into THIS CTA's shared memory that completes on an mbarrier of EITHER CTA of the pair (.cta_group::2): the
+// peer's weight half lands in the peer's shared memory and signals the leader's w_full.  Without the qualifier the barrier
+// has to live in the destination CTA.
+__device__ __forceinline__ void tma_load_2d_to(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cwait_cluster(uint64_t* b, uint32_t parity, int role, int what, int link, int chunk) {
+  uint32_t ok = 0, spins = 0;
+  const uint32_t addr = smem_u32(b);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > tc::kSpinLimit) chain_timeout(role, what, link, chunk);
+  }
+}
+
+template <int SWEEP>
+__global__ void __launch_bounds__(Cfg2::NUM_THREADS, 1)
+chain2_kernel(const __grid_constant__ Maps tm, const Args a) {
+  using C = Cfg2;
+  constexpr bool X3 = true;
+  constexpr int OS = C::O_STAGES, IS = C::I_STAGES, WS = C::W_STAGES, EW = C::EPI_WARPS, CW = C::CW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wring = smem;
+  uint8_t* oring = smem + WS * C::W_STAGE;
+  uint8_t* iring = oring + OS * C::O_STAGE;
+  uint8_t* extra = iring + IS * C::I_STAGE;
+  uint64_t* bars = (uint64_t*)extra;
+  uint64_t* w_full = bars;           // [WS]  LEADER's copy: both CTAs' weight halves landed (TMA of both completes here)
+  uint64_t* w_empty = bars + 2;      // [WS]  local: the pair's MMAs that read the stage completed (multicast commit)
+  uint64_t* a_ready = bars + 4;      // [OS]  LEADER's copy: both CTAs' teams have written the chunk (2 arrivals)
+  uint64_t* a_loc = bars + 6;        // [OS]  local: this CTA's team has written the chunk -> store warp
+  uint64_t* o_free = bars + 8;       // [OS]  local: multicast commit + this CTA's store warp
+  uint64_t* in_full = bars + 10;     // [IS]  local: input chunks landed
+  uint64_t* in_free = bars + 12;     // [IS]  local: the team has consumed them
+  uint64_t* acc_full = bars + 14;    // [2]   local: multicast commit
+  uint64_t* acc_empty = bars + 16;   // [2]   LEADER's copy: both CTAs' teams drained the accumulator (2 arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+  float* ypart = (float*)(extra + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc2::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < a.nlinks; ++i) {
+      const LinkD& L = a.link[i];
+      if (L.in0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.in0[i]) : "memory");
+      if (L.in2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.in2[i]) : "memory");
+      if (L.out0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.out0[i]) : "memory");
+      if (L.out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.out2[i]) : "memory");
+      if (L.feeds) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.whi[i]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.wlo[i]) : "memory");
+      }
+    }
+    for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < OS; ++i) tc::mbar_init(&a_ready[i], 2), tc::mbar_init(&a_loc[i], 1), tc::mbar_init(&o_free[i], 2);
+    for (int i = 0; i < IS; ++i) tc::mbar_init(&in_full[i], 1), tc::mbar_init(&in_free[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  tc2::cluster_sync_all();           // both CTAs' barriers initialised, TMEM allocated
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  tc::pdl_trigger();
+  tc::pdl_wait();
+
+  if (warp == 0) {
+    // ===================== weight producer: this CTA's half of every k-block, completing on the LEADER's barrier ====
+    if (lane == 0) {
+      uint32_t ws = 0, wph = 0;
+      uint32_t wf_leader[WS];
+#pragma unroll
+      for (int i = 0; i < WS; ++i)
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(wf_leader[i]) : "r"(smem_u32(&w_full[i])), "r"(0u));
+      for (int tile = cid; tile < a.ntiles; tile += ncl) {
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          if (!L.feeds) continue;
+          const int nch = L.width >> 5, N = L.n_next, NH = N >> 1;
+          for (int j = 0; j < nch; ++j) {
+            cwait(&w_empty[ws], wph ^ 1, 0, 0, i, j);
+            uint8_t* dst = wring + ws * C::W_STAGE;
+            const uint32_t bar = ws == 0 ? wf_leader[0] : wf_leader[1];
+            if (leader) tc::mbar_expect_tx(&w_full[ws], (uint32_t)N * 256u);   // both halves, hi + lo
+            if (L.b_mn) {
+              for (int c = 0; c < NH / 32; ++c) {
+                tma_load_2d_to(dst + c * 4096, &tm.whi[i], bar, NH * (int)rank + 32 * c, 32 * j);
+                tma_load_2d_to(dst + 16384 + c * 4096, &tm.wlo[i], bar, NH * (int)rank + 32 * c, 32 * j);
+              }
+            } else {
+              tma_load_2d_to(dst, &tm.whi[i], bar, 32 * j, NH * (int)rank);
+              tma_load_2d_to(dst + 16384, &tm.wlo[i], bar, 32 * j, NH * (int)rank);
+            }
+            if (++ws == WS) ws = 0, wph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== input producer (own 128 rows): runs IS chunks ahead of the epilogue =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = cid; tile < a.ntiles; tile += ncl) {
+        const int m0 = tile * 256 + 128 * (int)rank;
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          if (!(L.in0 || L.in2)) continue;
+          const int nch = L.width >> 5;
+          for (int j = 0; j < nch; ++j) {
+            cwait(&in_free[s], ph ^ 1, 2, 0, i, j);
+            uint8_t* st = iring + s * C::I_STAGE;
+            tc::mbar_expect_tx(&in_full[s], (uint32_t)CHUNK_BYTES * (uint32_t)((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0)));
+            if (L.in0) tc::tma_load_2d(st, &tm.in0[i], &in_full[s], 32 * j, m0);
+            if (L.in2) tc::tma_load_2d(st + CHUNK_BYTES, &tm.in2[i], &in_full[s], 32 * j, m0);
+            if (++s == IS) s = 0, ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      uint32_t s = 0, ph = 0, ws = 0, wph = 0, mm = 0;
+      for (int tile = cid; tile < a.ntiles; tile += ncl) {
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          const int nch = L.width >> 5;
+          const uint32_t acc = mm & 1;
+          uint32_t idesc = 0;
+          if (L.feeds) {
+            cwait_cluster(&acc_empty[acc], ((mm >> 1) & 1) ^ 1, 1, 0, i, 0);
+            tc::tc_fence_after();
+            idesc = tc2::make_idesc_pair(L.n_next, false, L.b_mn != 0);
+          }
+          const uint32_t tmem_d = tmem_base + acc * 256;
+          for (int j = 0; j < nch; ++j) {
+            cwait_cluster(&a_ready[s], ph, 1, 1, i, j);
+            if (L.feeds) {
+              cwait_cluster(&w_full[ws], wph, 1, 2, i, j);
+              tc::tc_fence_after();
+              const uint32_t a0 = smem_u32(oring + s * C::O_STAGE);
+              const uint32_t alo = a0 + CHUNK_BYTES;
+              const uint32_t b0 = smem_u32(wring + ws * C::W_STAGE);
+              const uint32_t blo = b0 + 16384;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = tc::make_desc(a0 + k * 32, 16, 1024, 2);
+                const uint64_t dal = tc::make_desc(alo + k * 32, 16, 1024, 2);
+                const uint64_t db = L.b_mn ? tc::make_desc(b0 + k * 1024, 4096, 512, 1) : tc::make_desc(b0 + k * 32, 16, 1024, 2);
+                const uint64_t dbl = L.b_mn ? tc::make_desc(blo + k * 1024, 4096, 512, 1) : tc::make_desc(blo + k * 32, 16, 1024, 2);
+                tc2::umma_tf32_pair(tmem_d, dal, db, idesc, (j | k) ? 1u : 0u);
+                tc2::umma_tf32_pair(tmem_d, da, dbl, idesc, 1u);
+                tc2::umma_tf32_pair(tmem_d, da, db, idesc, 1u);
+              }
+              tc2::umma_commit_pair(&w_empty[ws]);
+              if (++ws == WS) ws = 0, wph ^= 1;
+            }
+            tc2::umma_commit_pair(&o_free[s]);
+            if (++s == OS) s = 0, ph ^= 1;
+          }
+          if (L.feeds) {
+            tc2::umma_commit_pair(&acc_full[acc]);
+            ++mm;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== store warp (own 128 rows) =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = cid; tile < a.ntiles; tile += ncl) {
+        const int m0 = tile * 256 + 128 * (int)rank;
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          const int nch = L.width >> 5;
+          for (int j = 0; j < nch; ++j) {
+            cwait(&a_loc[s], ph, 3, 0, i, j);
+            const uint8_t* st = oring + s * C::O_STAGE;
+            if (L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
+            if (L.out2) tma_store_2d(&tm.out2[i], st + C::B2_OFF, 32 * j, m0);
+            if (L.out0 || L.out2) {
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            tc::mbar_arrive(&o_free[s]);
+            if (++s == OS) s = 0, ph ^= 1;
+          }
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // ===================== epilogue team (own 128 rows, own TMEM lanes) =====================
+    const int e = warp - C::EPI_WARP0;
+    const int q = warp & 3;
+    const int h = e >> 2;
+    const int rt = q * 32 + lane;
+    const bool elected = e == 0 && lane == 0;
+    uint32_t so = 0, pho = 0, si = 0, phi = 0, mmr = 0;
+    bool first_tile = true;
+    for (int tile = cid; tile < a.ntiles; tile += ncl, first_tile = false) {
+      const int row = tile * 256 + 128 * (int)rank + rt;
+      const bool valid = row < a.rows;
+      float yb = 0.f, yacc = 0.f;
+      if (SWEEP == SWEEP_T) yb = valid ? __ldg(a.ybar + row) : 0.f;
+      for (int i = 0; i < a.nlinks; ++i) {
+        const LinkD& L = a.link[i];
+        const int nch = L.width >> 5;
+        const bool has_acc = L.kind != LINK_FIRST;
+        const bool has_in = L.in0 || L.in2;
+        const uint32_t acc = mmr & 1;
+        if (has_acc) {
+          cwait(&acc_full[acc], (mmr >> 1) & 1, 4, 0, i, 0);
+          tc::tc_fence_after();
+        }
+        for (int j = 0; j < nch; ++j) {
+          if (has_in) cwait(&in_full[si], phi, 4, 1, i, j);
+          cwait(&o_free[so], pho ^ 1, 4, 2, i, j);      // MMAs + store of the chunk two positions back are done with it
+          const float* i0 = (const float*)(iring + si * C::I_STAGE);
+          const float* i2 = i0 + CHUNK_BYTES / 4;
+          float* b0 = (float*)(oring + so * C::O_STAGE);
+          float* b1 = b0 + CHUNK_BYTES / 4;
+          float* b2 = (float*)(oring + so * C::O_STAGE + C::B2_OFF);
+          uint32_t v[CW];
+          if (has_acc) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (uint32_t)(32 * j + h * CW);
+            tmem_ld_cols<CW>(taddr, v);
+          }
+          const int c0 = 32 * j;
+          chunk_math<SWEEP, X3, CW, false>(a, L, i, c0, rt, h * (CW / 4), i0, i2, b0, b1, b2, v, yb, yacc);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc::tc_fence_before();
+          named_bar(1, 32 * EW);                         // the chunk is written, its inputs are consumed
+          if (L.colsum) {
+            if (h == 0) chunk_colsum(a, L, i, c0, q, lane, b0, b2, first_tile);
+            named_bar(1, 32 * EW);                       // ... and read back: the stage may be handed on
+          }
+          // ONE thread signals: the input producer and the store warp of this CTA, and the leader's MMA issuer (a
+          // cluster-scope release arrive is a gpu-wide fence, so the peer does it once per chunk, not once per warp)
+          if (elected) {
+            if (has_in) tc::mbar_arrive(&in_free[si]);
+            tc::mbar_arrive(&a_loc[so]);
+            if (leader) tc::mbar_arrive(&a_ready[so]);
+            else tc2::mbar_arrive_cta(&a_ready[so], 0);
+          }
+          if (has_in && ++si == IS) si = 0, phi ^= 1;
+          if (++so == OS) so = 0, pho ^= 1;
+        }
+        if (has_acc) {
+          // every warp's tcgen05.ld of this accumulator completed before the chunk barrier above
+          if (elected) {
+            if (leader) tc::mbar_arrive(&acc_empty[acc]);
+            else tc2::mbar_arrive_cta(&acc_empty[acc], 0);
+          }
+          ++mmr;
+        }
+        if (SWEEP == SWEEP_F && L.kind == LINK_LAST) {
+          if (h > 0) ypart[(h - 1) * 128 + rt] = yacc;
+          named_bar(1, 32 * EW);
+          if (h == 0 && valid) {
+            float y = yacc;
+#pragma unroll
+            for (int hh = 1; hh < EW / 4; ++hh) y += ypart[(hh - 1) * 128 + rt];
+            a.Y[row] = y + __ldg(a.bout);
+          }
+          named_bar(1, 32 * EW);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  tc2::cluster_sync_all();           // no CTA leaves (or frees TMEM) while its peer may still touch it
+  if (warp == 1) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -485,6 +885,24 @@ inline cudaError_t launch_chain(const Maps& m, const Args& a, int num_sms, cudaS
   const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;
   return tc::launch_pdl(kern, grid, C::NUM_THREADS, C::SMEM_BYTES, st, 1, m, a);
 }
+
+// CTA-pair launch: a.ntiles = number of 256-row tiles; grid = 2 x min(tiles, SMs / 2), cluster (2,1,1)
+template <int SWEEP>
+inline cudaError_t launch_chain2(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {
+  using C = Cfg2;
+  auto kern = chain2_kernel<SWEEP>;
+  static unsigned long long attr_devs = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
+  if (!((attr_devs >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_devs |= 1ull << dev;
+  }
+  const int pairs = a.ntiles < num_sms / 2 ? a.ntiles : num_sms / 2;
+  return tc::launch_pdl(kern, 2 * pairs, C::NUM_THREADS, C::SMEM_BYTES, st, 2, m, a);
+}
+inline int chain2_grid(int ntiles2, int num_sms) { return 2 * (ntiles2 < num_sms / 2 ? ntiles2 : num_sms / 2); }
 
 }  // namespace chain
 }  // namespace fbsnn

@@ -848,6 +848,37 @@ __global__ void peer_wait_kernel(const float* local_buf, long long flag_off, int
     peer_spin(reinterpret_cast<const unsigned*>(local_buf + flag_off) + kPeerMaxWorld + threadIdx.x, epoch);
 }
 
+// ----------------------------------------------------------------------------------------------------
+// min_loss_state of the reference's train() (with_corr_high_dimension_pde.py:431-433) without a host round trip:
+//   if loss < best: best = loss, best_iter = iter, (X, Y) -> (X_best, Y_best)
+// track_min_decide (1 thread) sets the flag, track_min_copy copies only when it is set (no traffic otherwise); the
+// comparison is false for a NaN loss, like the reference's `loss < min_loss`.
+// state (32 bytes): [0] best loss (float, +inf initially) | [1] flag (int) | [2] best call index (int, -1) | [3] call
+// counter (int) | [4..5] int64: Philox iteration the best step drew its increments with (opt_state's counter - 1)
+// ----------------------------------------------------------------------------------------------------
+__global__ void track_min_decide_kernel(const float* __restrict__ loss, float* __restrict__ state,
+                                        const OptState* __restrict__ opt) {
+  int* st = reinterpret_cast<int*>(state);
+  const float l = loss[0];
+  const bool better = l < state[0];
+  st[1] = better ? 1 : 0;
+  if (better) {
+    state[0] = l, st[2] = st[3];
+    if (opt) *reinterpret_cast<long long*>(state + 4) = opt->rng_iter - 1;   // the optimiser step already advanced it
+  }
+  st[3] += 1;
+}
+__global__ void track_min_copy_kernel(const float* __restrict__ state, const float4* __restrict__ X,
+                                      float4* __restrict__ Xb, long long nX4, const float4* __restrict__ Y,
+                                      float4* __restrict__ Yb, long long nY4) {
+  if (reinterpret_cast<const int*>(state)[1] == 0) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nX4 + nY4; i += stride) {
+    if (i < nX4) Xb[i] = X[i];
+    else Yb[i - nX4] = Y[i - nX4];
+  }
+}
+
 __global__ void opt_prepare_kernel(const float* __restrict__ part, int npart, FbsnnAdam hp, OptState* st) {
   __shared__ double red[32];
   double acc = 0.0;

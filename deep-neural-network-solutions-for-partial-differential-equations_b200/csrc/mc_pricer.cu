@@ -281,6 +281,80 @@ mc_paths_kernel(const McK k, const float* __restrict__ S0, const float* __restri
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------
+// Closed-form comparators the reference's drivers plot the learned Y against, evaluated for
+// a whole prediction tensor in one launch instead of Python loops over (sample, step):
+//   mode 0  BasketOptionPriceCalculator.calculate_option_prices (nd_BSPDE_case.py:621-658): Black-Scholes call per
+//           (row, asset) with time to maturity T - t[row], then the equal-weighted mean over the assets
+//   mode 1  BasicOptionPriceCalculator.calculate_call_option_prices (with_corr_high_dimension_pde.py:663-700): one
+//           Black-Scholes call per (row, col) on the basket average with volatility sigma / sqrt(D) and time to maturity
+//           T - time[min(col, ntimes - 1)]; at maturity the payoff and its one-sided delta
+// Same IEEE behaviour as the reference formulas (tau = 0 in mode 0 gives d1 = +-inf, i.e. the intrinsic value).
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double norm_cdf(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+__device__ __forceinline__ void bs_call(double S, double K, double tau, double r, double sigma, double& price, double& delta) {
+  const double sq = sigma * sqrt(tau);
+  const double d1 = (log(S / K) + (r + 0.5 * sigma * sigma) * tau) / sq;
+  const double d2 = d1 - sq;
+  delta = norm_cdf(d1);
+  price = S * delta - K * exp(-r * tau) * norm_cdf(d2);
+}
+__global__ void bs_comparator_kernel(int mode, const double* __restrict__ S, const double* __restrict__ t, long long rows,
+                                     int cols, int ntimes, double K, double r, double sigma, double T, int dims,
+                                     double* __restrict__ price_out, double* __restrict__ delta_out) {
+  if (mode == 0) {   // one warp per row, lanes over assets, fixed-order warp reduction
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double tau = T - t[row];
+    double ps = 0.0, ds = 0.0;
+    for (int a = lane; a < cols; a += 32) {
+      double p, d;
+      bs_call(S[row * cols + a], K, tau, r, sigma, p, d);
+      ps += p, ds += d;
+    }
+    ps = warp_sum(ps), ds = warp_sum(ds);
+    if (lane == 0) price_out[row] = ps / cols, delta_out[row] = ds / cols;
+  } else {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int j = (int)(i % cols);
+    const double tau = T - t[j < ntimes ? j : ntimes - 1];
+    const double s = S[i];
+    double p, d;
+    if (tau > 0.0) {
+      bs_call(s, K, tau, r, sigma / sqrt((double)dims), p, d);
+    } else {
+      p = fmax(s - K, 0.0);
+      d = s > K ? 1.0 : (s == K ? 0.5 : 0.0);
+    }
+    price_out[i] = p, delta_out[i] = d;
+  }
+}
+
+// Roofline denominator of the pricer: nothing but the generator -- Philox4x32-10 with
+// register-resident round keys + the MUFU Box-Muller of normal4() -- at full occupancy, every normal consumed by one
+// add.  bench.py times this probe on the same GPU and reports the pricer's normals/s as a fraction of it.
+__global__ void __launch_bounds__(256, 4)
+normal_rate_probe_kernel(unsigned long long blocks_per_thread, uint64_t seed, double* __restrict__ part) {
+  const PhiloxKeys keys = philox_keys((uint32_t)seed, (uint32_t)(seed >> 32));
+  const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  Philox4 ctr{(uint32_t)t, (uint32_t)(t >> 32), 0u, 0u};
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 2
+  for (unsigned long long i = 0; i < blocks_per_thread; ++i) {
+    float z[4];
+    ctr.z = (uint32_t)i, ctr.w = (uint32_t)(i >> 32);
+    normal4(philox4x32_10(ctr, keys), z);
+    acc0 += z[0] + z[1];
+    acc1 += z[2] + z[3];
+  }
+  __shared__ double red[32];
+  const double bs = block_sum((double)(acc0 + acc1), red);
+  if (threadIdx.x == 0) part[blockIdx.x] = bs;
+}
+
 }  // namespace fbsnn
 
 using namespace fbsnn;
@@ -379,6 +453,36 @@ int mc_hjb_exact(int32_t D, int32_t n_times, const float* t, const float* X, flo
   hjb_exact_final_kernel<<<n_times, 128, 0, st>>>((const double*)scratch, bx, n_mc, u_out);
   if (cudaGetLastError() != cudaSuccess) return FBSNN_E_CUDA;
   g_mc_launches += 2;
+  return 0;
+}
+
+// Measurement hook: draws ~n_normals standard normals with the pricer's generator and nothing else (see
+// normal_rate_probe_kernel); *normals_out = the exact count drawn.  The caller times it with CUDA events.
+int mc_normal_rate_probe(uint64_t n_normals, uint64_t seed, void* scratch, uint64_t* normals_out, void* stream) {
+  if (!scratch || !normals_out || n_normals == 0) return FBSNN_E_BADARG;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+    return FBSNN_E_CUDA;
+  const int blocks = std::min(sms * 8, kMcMaxBlocks);
+  const unsigned long long threads = (unsigned long long)blocks * 256;
+  const unsigned long long per_thread = std::max<unsigned long long>(1, n_normals / (4 * threads));
+  normal_rate_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(per_thread, seed, (double*)scratch);
+  if (cudaGetLastError() != cudaSuccess) return FBSNN_E_CUDA;
+  *normals_out = 4ull * per_thread * threads;
+  g_mc_launches += 1;
+  return 0;
+}
+
+int mc_bs_comparator(int32_t mode, const double* S, const double* t, int64_t rows, int32_t cols, int32_t ntimes, double K,
+                     double r, double sigma, double T, int32_t dims, double* price_out, double* delta_out, void* stream) {
+  if ((mode != 0 && mode != 1) || !S || !t || rows < 1 || cols < 1 || !price_out || !delta_out || (mode == 1 && (ntimes < 1 || dims < 1)))
+    return FBSNN_E_BADARG;
+  const long long threads = mode == 0 ? (long long)rows * 32 : (long long)rows * cols;
+  bs_comparator_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mode, S, t, rows, cols, ntimes, K, r,
+                                                                                         sigma, T, dims, price_out, delta_out);
+  if (cudaGetLastError() != cudaSuccess) return FBSNN_E_CUDA;
+  g_mc_launches += 1;
   return 0;
 }
 

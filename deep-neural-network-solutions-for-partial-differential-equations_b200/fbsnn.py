@@ -214,19 +214,20 @@ class FBSNN(ABC):
         W = torch.from_numpy(np.cumsum(DW, axis=1)).float().to(self.device)
         return t, W
 
-    def fetch_minibatch_device(self, seed=None, iteration=0, path_offset=0, n_paths=None):
+    def fetch_minibatch_device(self, seed=None, iteration=0, path_offset=0, n_paths=None, N=None):
         """Device-side twin of fetch_minibatch(): same layout and distribution (incl. the Cholesky-correlated form),
         drawn by Philox4x32-10 keyed (seed, iteration, GLOBAL path id) -- so any contiguous shard
         [path_offset, path_offset + n_paths) reproduces exactly the rows of the full minibatch.  Not NumPy's
         stream."""
         lib = self._require_cuda()
         M = self.M if n_paths is None else int(n_paths)
-        sp = self._spec()
+        N = self.N if N is None else int(N)
+        sp = self._spec(N)
         dev = self.device
         with torch.cuda.device(dev):
             ws = self._workspace(lib, sp, M, True)
-            t = torch.empty(M, self.N + 1, 1, device=dev)
-            W = torch.empty(M, self.N + 1, self.D, device=dev)
+            t = torch.empty(M, N + 1, 1, device=dev)
+            W = torch.empty(M, N + 1, self.D, device=dev)
             chol = self._chol_device()
             rc = lib.fbsnn_fetch_minibatch(ctypes.byref(sp), float(self.T), M, int(path_offset),
                                            int(self.seed if seed is None else seed), int(iteration), _ptr(chol),
@@ -427,40 +428,49 @@ class FBSNN(ABC):
         loss_buf = torch.zeros(N_Iter + 1, device=dev)
         y0_buf = torch.zeros(N_Iter + 1, device=dev)
         time_logs = []
-        min_loss, min_loss_state = float("inf"), None
         cumulative, start = 0.0, time.time()
         last_logged = 0
         with torch.cuda.device(dev):
+            track = self._begin_min_tracking() if track_min else None
             for k, it in enumerate(range(previous_it, previous_it + N_Iter)):
                 if self.n_schedule == "reference":
-                    self.N = self._scheduled_N(it)
+                    n_new = self._scheduled_N(it)
+                    if n_new != self.N:
+                        self.N = n_new
+                        if track is not None:        # the trajectories change shape: keep the best so far, re-arm
+                            self._flush_min_tracking(track)
                 if self.brownian == "numpy":
                     t_b, W_b = self.fetch_minibatch()
                 else:
                     t_b = W_b = None
-                X, Y = self._step(t_b, W_b, loss_buf[k:k + 1], track_min, k)
+                # the loss, Y0 and the min-loss bookkeeping (with_corr...:428-433) all stay on the device: nothing is
+                # read back between the reference's logging points
+                X, Y = self._step(t_b, W_b, loss_buf[k:k + 1], track is not None and track["keep_X"], k, track=track)
                 y0_buf[k] = Y[0, 0, 0]
-                if track_min:   # reference semantics: a host read of the loss every iteration (with_corr...:431-433)
-                    lv = float(loss_buf[k])
-                    if lv < min_loss:
-                        min_loss = lv
-                        min_loss_state = (X.clone().detach(), Y.clone().detach())
                 if it % self._log_every == 0:
                     vals = loss_buf[last_logged:k + 1].cpu().numpy()
                     last_logged = k + 1
                     elapsed = time.time() - start
                     cumulative += elapsed
                     time_logs.append(cumulative)
+                    if self._skip_nonfinite and not np.isfinite(vals[-1]):
+                        # heston_dnnpde.py:408-410 `continue`s on a NaN loss: that iteration is neither averaged nor logged
+                        last_logged = k + 1 - int(np.isfinite(vals).sum())   # keep the finite ones for the next window
+                        start = time.time()
+                        continue
                     if self._arity == "short":
                         print('It: %d, Loss: %.3e, Y0: %.3f, Time: %.2f, Learning Rate: %.3e' %
                               (it, float(vals[-1]), float(y0_buf[k]), elapsed, learning_rate))
                     start = time.time()
+                    if self._skip_nonfinite:
+                        vals = vals[np.isfinite(vals)]
                     self.training_loss.append(vals.mean())
                     self.iteration.append(it)
                     if self._train_returns == "heston":
                         self.Y0_values.append(float(y0_buf[k]))
             self.last_losses = loss_buf[:N_Iter].cpu().numpy()     # device -> host read of the step results
             self.last_Y0 = y0_buf[:N_Iter].cpu().numpy()
+            min_loss, min_loss_state = self._finish_min_tracking(track) if track is not None else (float("inf"), None)
         # p.grad = the gradient the last Adam step used (summed over ranks on the multi-GPU peer path)
         self._fp.attach_grads(self._peer["sum"][:self._fp.n] if self._peer is not None else None)
         if self._train_returns == "heston":               # heston_dnnpde.py:448
@@ -471,6 +481,93 @@ class FBSNN(ABC):
         if self._train_returns == "triple":
             return graph, min_loss, min_loss_state
         return graph, min_loss, min_loss_state, time_logs
+
+    # ------------------------------------------------------------------------------------------------
+    # min_loss / min_loss_state (with_corr...:431-433) without a per-iteration host sync
+    # ------------------------------------------------------------------------------------------------
+    def _begin_min_tracking(self):
+        """Device-side record of the best iteration: fbsnn_track_min keeps (best loss, its iteration index) and copies
+        the trajectories of an improving iteration on the device.  With in-kernel Brownian increments X does not depend
+        on the parameters, so only Y (M x (N+1) floats) is copied and X is re-materialised once, at the end, from the
+        Philox (seed, iteration) of the best step; with host-supplied increments X is copied too."""
+        state = torch.zeros(8, device=self.device)
+        self._reset_track_state(state)
+        return {"state": state, "keep_X": self.brownian == "numpy", "Xb": None, "Yb": None, "N": None,
+                "best": (float("inf"), None), "shard": self._shard()}
+
+    @staticmethod
+    def _reset_track_state(state):
+        state[0] = float("inf")
+        state[1:4].view(torch.int32).copy_(torch.tensor([0, -1, 0], dtype=torch.int32))
+
+    def _track_buffers(self, track, X, Y):
+        if track["N"] != self.N or track["Yb"] is None:
+            track["N"] = self.N
+            track["Yb"] = torch.zeros_like(Y)
+            track["Xb"] = torch.zeros_like(X) if (track["keep_X"] and X is not None) else None
+        return track["Xb"], track["Yb"]
+
+    def _enqueue_track(self, lib, track, loss, X, Y):
+        Xb, Yb = self._track_buffers(track, X, Y)
+        n_x = X.numel() if Xb is not None else 0
+        if n_x % 4 or Y.numel() % 4:              # odd sizes: host-free fallback with torch ops on the device
+            better = loss.reshape(()) < track["state"][0]
+            track["state"][0] = torch.where(better, loss.reshape(()), track["state"][0])
+            Yb.copy_(torch.where(better, Y, Yb))
+            if Xb is not None:
+                Xb.copy_(torch.where(better, X, Xb))
+            ints = track["state"][1:4].view(torch.int32)
+            ints[1] = torch.where(better, ints[2], ints[1])
+            ints[2] += 1
+            it64 = track["state"][4:6].view(torch.int64)
+            it64[0] = torch.where(better, self._opt_state[24:32].view(torch.int64)[0] - 1, it64[0])
+            return
+        _lib.check(lib.fbsnn_track_min(_ptr(loss), _ptr(track["state"]), _ptr(self._opt_state), _ptr(X) if n_x else None,
+                                       _ptr(Xb) if n_x else None, n_x, _ptr(Y), _ptr(Yb), Y.numel(), self._stream()),
+                   "fbsnn_track_min")
+
+    def _flush_min_tracking(self, track):
+        """Fold the device record into the running best (called when N changes, and at the end of train())."""
+        if track["Yb"] is None:
+            return
+        host = track["state"].cpu()
+        best = float(host[0])
+        k_best = int(host[1:4].view(torch.int32)[1])
+        rng_best = int(host[4:6].view(torch.int64)[0])
+        if k_best >= 0 and best < track["best"][0]:
+            Yb = track["Yb"].clone()
+            if track["keep_X"]:
+                Xb = track["Xb"].clone()
+            else:   # X of the best step from its Philox stream: (seed, device iteration counter at that step)
+                Xb = self._paths_philox(rng_best, track["N"], *track["shard"])
+            track["best"] = (best, (Xb.detach(), Yb.detach()))
+        self._reset_track_state(track["state"])
+        track["Yb"] = None
+
+    def _finish_min_tracking(self, track):
+        self._flush_min_tracking(track)
+        return track["best"]
+
+    def _paths_philox(self, iteration, N, lo, hi):
+        """X (m_loc, N+1, D) of the training step that drew its increments with Philox `iteration`: X does not depend
+        on the parameters, so it is re-materialised exactly by one more evaluation of that step's kernels (gradients
+        into a scratch buffer) instead of having been copied on every improving iteration."""
+        lib = self._require_cuda()
+        fp, dev = self._fp, self.device
+        sp = self._spec(N)
+        m_loc = hi - lo
+        ws = self._workspace(lib, sp, m_loc, True)
+        X = torch.empty(m_loc, N + 1, self._sdim, device=dev)
+        scratch = torch.empty(fp.n, device=dev)
+        loss = torch.empty((), device=dev)
+        Xi = self._state_xi(self.Xi.detach())
+        xi_loc = Xi.contiguous() if Xi.shape[0] == 1 else Xi[lo:hi].contiguous()
+        chol = self._chol_device()
+        rc = lib.fbsnn_loss_grad(ctypes.byref(sp), _ptr(fp.flat), _ptr(scratch), None, None, _ptr(xi_loc), xi_loc.shape[0],
+                                 m_loc, float(self.T), lo, self.seed & 0xFFFFFFFFFFFFFFFF, int(iteration), _ptr(chol),
+                                 _ptr(ws), ws.numel(), _ptr(X), None, None, _ptr(loss), self._stream())
+        _lib.check(rc, "fbsnn_loss_grad")
+        return X
 
     def begin_training(self, learning_rate):
         """Fresh Adam state, as the reference builds a new optimiser in every train() call."""
@@ -484,46 +581,82 @@ class FBSNN(ABC):
                                1.0 if self._skip_nonfinite else 0.0)
         self._n_train_calls += 1
 
-    def _step(self, t_b, W_b, loss_out, want_X, k, alias_inputs=False):
-        """training_step through a captured CUDA graph when possible (single GPU): the ~38 kernels of an iteration
-        are replayed with one launch, which is what bounds small-M steps.  The Adam step and Philox iteration
-        counters live on the device, so a replay is a genuinely new iteration."""
-        if not self.use_cuda_graph or (self.data_parallel and parallel.is_distributed()):
-            return self.training_step(t_b, W_b, loss_out, want_X=want_X, iteration=k)
+    _MAX_GRAPHS = 6
+
+    def _step(self, t_b, W_b, loss_out, want_X, k, alias_inputs=False, track=None):
+        """training_step through a captured CUDA graph when possible: the ~20-40 kernels of an iteration are replayed
+        with one launch, which is what bounds small-M steps.  The Adam step and Philox iteration counters live on the
+        device, so a replay is a genuinely new iteration.  Multi-GPU steps are captured too when the gradient exchange
+        is the library's own peer-memory kernel (its cross-GPU barrier is keyed by the same device counter); the NCCL
+        exchange stays eager.  `track` = device-side min-loss bookkeeping enqueued right after the step (in the graph)."""
+        lib = self._require_cuda()
+        dp = self.data_parallel and parallel.is_distributed()
+        if dp and self.collective == "peer":
+            self._peer_buffers()                  # may fall back to "nccl" (agreed across ranks)
+        if not self.use_cuda_graph or (dp and self.collective != "peer"):
+            X, Y = self.training_step(t_b, W_b, loss_out, want_X=want_X)
+            if track is not None:
+                self._enqueue_track(lib, track, loss_out, X, Y)
+            return X, Y
         host_batch = W_b is not None
+        # everything a captured kernel argument depends on: shapes, hyper-parameters baked in by value (lr, clip, T, seed)
+        # and the addresses of tensors the caller may replace (Xi, the aliased minibatch, the tracking buffers)
         key = (self.M, self.N, self.precision, bool(want_X), host_batch, self._hp.lr, self._hp.max_grad_norm,
-               self.seed, (t_b.data_ptr(), W_b.data_ptr()) if (alias_inputs and host_batch) else None)
+               self.seed, float(self.T), self.Xi.data_ptr(), id(track["state"]) if track is not None else None,
+               (t_b.data_ptr(), W_b.data_ptr()) if (alias_inputs and host_batch) else None)
         gs = self._graphs.get(key)
         if gs is None:
             dev = self.device
+            while len(self._graphs) >= self._MAX_GRAPHS:      # bounded: an N-schedule or many lr values would otherwise
+                self._graphs.pop(next(iter(self._graphs)))    # pin one set of X / Y outputs per key for ever
             gs = {"loss": torch.zeros(1, device=dev)}
             if host_batch and alias_inputs:     # caller keeps (t_b, W_b) alive and in place: read them directly
                 gs["t"], gs["W"] = t_b, W_b
             elif host_batch:
                 gs["t"], gs["W"] = torch.empty_like(t_b), torch.empty_like(W_b)
                 gs["t"].copy_(t_b), gs["W"].copy_(W_b)
-            # capture needs a warm-up run on a side stream; keep it side-effect free by restoring the state
+            # capture needs a warm-up run on a side stream; keep it side-effect free by restoring the state.  The Philox
+            # iteration counter (bytes 24..32 of the optimiser state) is restored on one GPU only: on several GPUs it is
+            # also the epoch of the peer barrier, which must never run backwards (every rank advances it alike)
             fp = self._fp
             saved = [x.clone() for x in (fp.flat, fp.exp_avg, fp.exp_avg_sq, self._opt_state)]
+            tsaved = track["state"].clone() if track is not None else None
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                self.training_step(gs.get("t"), gs.get("W"), gs["loss"], want_X=want_X)
+                Xw, Yw = self.training_step(gs.get("t"), gs.get("W"), gs["loss"], want_X=want_X)
+                if track is not None:
+                    self._track_buffers(track, Xw, Yw)
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 gs["X"], gs["Y"] = self.training_step(gs.get("t"), gs.get("W"), gs["loss"], want_X=want_X)
-            for dst, src in zip((fp.flat, fp.exp_avg, fp.exp_avg_sq, self._opt_state), saved):
+                if track is not None:
+                    self._enqueue_track(lib, track, gs["loss"], gs["X"], gs["Y"])
+                    gs["track_N"] = track["N"]
+            for dst, src in zip((fp.flat, fp.exp_avg, fp.exp_avg_sq), saved):
                 dst.copy_(src)
+            if dp:
+                rng_now = self._opt_state[24:32].clone()
+                self._opt_state.copy_(saved[3])
+                self._opt_state[24:32].copy_(rng_now)
+            else:
+                self._opt_state.copy_(saved[3])
+            if track is not None:
+                track["state"].copy_(tsaved)
             gs["graph"] = graph
             self._graphs[key] = gs
+        if track is not None and (track["Yb"] is None or track["N"] != self.N):
+            # tracking buffers were re-armed (N changed and came back): the captured copies point at the old ones
+            self._graphs.pop(key, None)
+            return self._step(t_b, W_b, loss_out, want_X, k, alias_inputs, track)
         if host_batch and not alias_inputs:
             gs["t"].copy_(t_b), gs["W"].copy_(W_b)
         gs["graph"].replay()
         loss_out.copy_(gs["loss"])
         return gs["X"], gs["Y"]
 
-    def training_step(self, t_b, W_b, loss_out, want_X=False, iteration=0):
+    def training_step(self, t_b, W_b, loss_out, want_X=False, iteration=None):
         """One training iteration, enqueued on the current stream without synchronising.  (t_b, W_b) are the
         GLOBAL minibatch in the reference layout, or None to draw the Brownian increments in-kernel (Philox).
         With data_parallel and torch.distributed initialised each rank evaluates its contiguous slice of the
@@ -564,11 +697,14 @@ class FBSNN(ABC):
                 loss_slot = peer["buf"][fp.n:fp.n + 1]
                 _lib.check(lib.fbsnn_peer_wait(_ptr(peer["buf"]), fp.n, parallel.world_size(), _ptr(self._opt_state),
                                                self._stream()), "fbsnn_peer_wait")
-            rc = lib.fbsnn_loss_grad(ctypes.byref(sp), _ptr(fp.flat), _ptr(fp.grad), _ptr(t_b), _ptr(W_b),
-                                     _ptr(xi_loc), xi_loc.shape[0], m_loc, float(self.T), lo, seed, iteration,
-                                     _ptr(chol), _ptr(ws), ws.numel(), _ptr(X), _ptr(Y), None, _ptr(loss_slot),
-                                     self._stream())
-            _lib.check(rc, "fbsnn_loss_grad")
+            # the Philox iteration is the persistent device counter of the optimiser state -- the same one the single-GPU
+            # fbsnn_train_step uses -- so the sharded step draws exactly the 1-GPU stream and consecutive train() calls
+            # (TrainingPhases) never replay noise
+            rc = lib.fbsnn_loss_grad_step(ctypes.byref(sp), _ptr(fp.flat), _ptr(fp.grad), _ptr(t_b), _ptr(W_b),
+                                          _ptr(xi_loc), xi_loc.shape[0], m_loc, float(self.T), lo, seed, _ptr(chol),
+                                          _ptr(self._opt_state), _ptr(ws), ws.numel(), _ptr(X), _ptr(Y),
+                                          _ptr(loss_slot), self._stream())
+            _lib.check(rc, "fbsnn_loss_grad_step")
             if peer:
                 # one kernel: cross-GPU barrier + sum of the peers' buffers over NVLink + clip norm; then Adam
                 rc = lib.fbsnn_peer_allreduce_adam(ctypes.byref(self._hp), _ptr(fp.flat),
@@ -589,10 +725,11 @@ class FBSNN(ABC):
         (fbsnn_peer_allreduce_adam).  torch's symmetric-memory allocator only provides the peer mapping; the
         barrier and the reduction are this library's kernel.  Falls back to NCCL if the devices cannot map each
         other's memory."""
-        if self._peer is not None:
+        if self._peer is not None or self.collective != "peer":
             return self._peer
+        import torch.distributed as dist
+        peer, err = None, None
         try:
-            import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
             lib = _lib.load()
             fp = self._fp
@@ -603,14 +740,21 @@ class FBSNN(ABC):
             buf.zero_()
             torch.cuda.synchronize(self.device)
             hdl = symm.rendezvous(buf, dist.group.WORLD)
-            dist.barrier()                     # every rank has zeroed its flags before anyone can signal
-            self._peer = {"buf": buf, "hdl": hdl, "ptrs": int(hdl.buffer_ptrs_dev),
-                          "sum": torch.zeros(fp.n + 4, device=self.device)}
-            fp.grad = buf[:fp.n]               # the gradient kernels now write straight into the shared buffer
-            fp.attach_grads()
+            peer = {"buf": buf, "hdl": hdl, "ptrs": int(hdl.buffer_ptrs_dev),
+                    "sum": torch.zeros(fp.n + 4, device=self.device)}
         except Exception as e:                 # noqa: BLE001 -- e.g. no P2P between the devices
+            err = e
+        # the choice between the peer kernel and NCCL must be the same on every rank (a rank that fell back alone would
+        # wait in an NCCL all-reduce for peers that spin in the peer kernel): agree on the minimum
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # also: every rank has zeroed its flags before anyone can signal
+        if int(ok) == 1:
+            self._peer = peer
+            self._fp.grad = peer["buf"][:self._fp.n]   # the gradient kernels now write straight into the shared buffer
+            self._fp.attach_grads()
+        else:
             import warnings
-            warnings.warn(f"symmetric memory unavailable ({e!r}); using the NCCL all-reduce")
+            warnings.warn(f"symmetric memory unavailable on at least one rank ({err!r}); using the NCCL all-reduce")
             self.collective = "nccl"
             self._peer = None
         return self._peer

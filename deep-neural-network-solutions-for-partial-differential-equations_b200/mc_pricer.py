@@ -53,8 +53,18 @@ def _device(device=None) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _draw_seed(seed: Optional[int]) -> int:
-    return int(seed) if seed is not None else int(np.random.randint(0, 2 ** 62))
+def _draw_seed(seed: Optional[int], shared: bool = False, device=None) -> int:
+    """Explicit seed, or one drawn from the NumPy global RNG.  `shared`: the pricer shards ONE global path range over
+    the ranks, so every rank must key Philox with the same seed -- rank 0's draw is broadcast (each rank still draws,
+    so the NumPy streams stay in step)."""
+    s = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 62))
+    if shared and seed is None and parallel.is_distributed():
+        import torch.distributed as dist
+        dev = _device(device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([s], dtype=torch.int64, device=dev)
+        dist.broadcast(t, src=0)
+        s = int(t.item())
+    return s
 
 
 class BlackScholesModel:
@@ -74,7 +84,11 @@ class BlackScholesModel:
         return torch.from_numpy(np.ascontiguousarray(L.T)).float().to(dev)
 
     def _mc_spec(self, T, N, strike=0.0) -> S.McSpec:
-        return S.McSpec(int(self.dimensions), int(N), float(self.rate), float(self.sigma), float(T), float(strike))
+        if np.ndim(self.sigma) != 0 and np.size(self.sigma) != 1:
+            raise NotImplementedError("the fused pricer takes one scalar volatility for all assets (what every driver of "
+                                      "the reference passes); per-asset sigma arrays are not implemented")
+        return S.McSpec(int(self.dimensions), int(N), float(self.rate), float(np.asarray(self.sigma).reshape(-1)[0]),
+                        float(T), float(strike))
 
     def generate_paths(self, S0, T, N, num_simulations, seed: Optional[int] = None, as_tensor: bool = False,
                        path_offset: int = 0, device=None):
@@ -153,7 +167,7 @@ class MonteCarloPricer:
         lib = _lib.load()
         m = self.model
         n_total = int(self.num_simulations)
-        seed = _draw_seed(self.seed)
+        seed = _draw_seed(self.seed, shared=self.data_parallel, device=self.device)
         self.last_seed = seed
         if self.data_parallel and parallel.is_distributed():
             lo, hi = parallel.shard_range(n_total, parallel.rank(), parallel.world_size())
@@ -189,7 +203,7 @@ class MonteCarloPricer:
         """exp(-rT) * mean payoff (:88-93).  `return_stderr=True` also returns the standard error, which the
         reference does not compute."""
         n_total = int(self.num_simulations)
-        seed = _draw_seed(self.seed)
+        seed = _draw_seed(self.seed, shared=self.data_parallel, device=self.device)
         self.last_seed = seed
         if self.data_parallel and parallel.is_distributed():
             lo, hi = parallel.shard_range(n_total, parallel.rank(), parallel.world_size())

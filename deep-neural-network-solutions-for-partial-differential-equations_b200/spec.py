@@ -5,7 +5,7 @@ import ctypes as C
 from dataclasses import dataclass
 
 MAX_HIDDEN = 8
-ABI_VERSION = 102          # fbsnn_version() of the library these struct mirrors were written against
+ABI_VERSION = 103          # fbsnn_version() of the library these struct mirrors were written against
 OPT_STATE_BYTES = 2048
 
 NET_FC, NET_NAIS = 0, 1

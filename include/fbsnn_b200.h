@@ -133,6 +133,24 @@ int fbsnn_loss_grad(const FbsnnSpec* spec, const float* params, float* grads, co
                     size_t workspace_bytes, float* X_out, float* Y_out, float* Z_out, float* loss_out,
                     void* stream);
 
+/* fbsnn_loss_grad for one rank of a data-parallel training step: the Philox iteration is the persistent device counter
+ * of `opt_state` (the one fbsnn_train_step uses; advanced by fbsnn_adam_step / fbsnn_peer_allreduce_adam), so that the
+ * sharded step draws exactly the single-GPU stream, consecutive train() calls never replay noise, and the call can
+ * be captured in a CUDA graph (no host-side iteration argument).  DeepBSDE.py:274-279 per rank. */
+int fbsnn_loss_grad_step(const FbsnnSpec* spec, const float* params, float* grads, const float* t, const float* W,
+                         const float* Xi, int64_t xi_rows, int64_t n_paths, float T, int64_t path_offset,
+                         uint64_t seed, const float* chol, const void* opt_state, void* workspace,
+                         size_t workspace_bytes, float* X_out, float* Y_out, float* loss_out, void* stream);
+
+/* min_loss / min_loss_state bookkeeping of the reference's train() (with_corr_high_dimension_pde.py:431-433,
+ * 1d_BSPDE_case.py:394-396) on the device: if *loss < state[0] then state[0] = *loss, the iteration index is recorded
+ * and (X, Y) are copied to (X_best, Y_best); nothing is copied otherwise and the host is never consulted.
+ * `state` = 32 bytes: float best loss (initialise to +inf), int flag, int best call index (-1), int call counter (0),
+ * int64 Philox iteration of the best step (taken from `opt_state`, nullable) -- with in-kernel increments X of that step
+ * can be re-materialised from it later instead of being copied.  n_x / n_y are element counts (multiples of 4; 0 skips). */
+int fbsnn_track_min(const float* loss, float* state, const void* opt_state, const float* X, float* X_best, int64_t n_x,
+                    const float* Y, float* Y_best, int64_t n_y, void* stream);
+
 /* clip_grad_norm_ + Adam.step on the flat buffers (with_corr_high_dimension_pde.py:424-425).  `opt_state` is
  * FBSNN_OPT_STATE_BYTES of device memory: int64 step counter at byte 0 (zero-initialised by the caller when the
  * optimizer is created -- the reference builds a fresh Adam per train() call, DeepBSDE.py:272), then float
@@ -198,6 +216,20 @@ int mc_basket_price_delta(const McSpec* spec, const float* S0, const float* weig
  * keyed by (seed, i, n).  t (n_times), X (n_times, D) device fp32; u_out (n_times) device double. */
 int mc_hjb_exact(int32_t D, int32_t n_times, const float* t, const float* X, float T, uint64_t n_mc, uint64_t seed,
                  void* scratch, double* u_out, void* stream);
+
+/* Measurement hook (bench.py): the pricer's generator alone -- Philox4x32-10 + MUFU Box-Muller,
+ * every normal consumed by one add -- drawing about n_normals normals; *normals_out = exact count.  Its rate on the
+ * same GPU is the roofline denominator of mc_basket_price.  No reference counterpart. */
+int mc_normal_rate_probe(uint64_t n_normals, uint64_t seed, void* scratch, uint64_t* normals_out, void* stream);
+
+/* Closed-form comparators of the reference's drivers for a whole prediction tensor in one launch (fp64).
+ * mode 0 replaces BasketOptionPriceCalculator.calculate_option_prices (nd_BSPDE_case.py:621-658): S (rows, cols = assets),
+ *        t (rows) -> price_out / delta_out (rows): mean over assets of the per-asset Black-Scholes call and delta.
+ * mode 1 replaces BasicOptionPriceCalculator.calculate_call_option_prices (with_corr_high_dimension_pde.py:663-700): S
+ *        (rows, cols) basket averages, t = time grid (ntimes) -> (rows, cols): Black-Scholes on the average with volatility
+ *        sigma / sqrt(dims), payoff and one-sided delta at maturity. */
+int mc_bs_comparator(int32_t mode, const double* S, const double* t, int64_t rows, int32_t cols, int32_t ntimes, double K,
+                     double r, double sigma, double T, int32_t dims, double* price_out, double* delta_out, void* stream);
 
 /* Replaces BlackScholesModel.generate_paths (:49-67): paths_out (n_paths, N+1, D) float32. */
 int mc_generate_paths(const McSpec* spec, const float* S0, const float* chol_T, uint64_t n_paths,

@@ -251,6 +251,94 @@ def run_basket_pricer_case():
     print(f"basket_pricer: price={price:.6f} shape={paths.shape}")
 
 
+def run_schedule_case():
+    """nd_BSPDE_case.CallOption.train() ITSELF with its N-schedule crossing iteration 4000: the
+    iteration counter is started at 3996 through the class's own resume mechanism (`previous_it = self.iteration[-1]`,
+    nd_BSPDE_case.py:326-328), so 8 iterations run at N = ceil(Mm) = 3, 3, 3, 3 and then N = ceil(Mm^2) = 5, 5, 5, 5.
+    Per-iteration losses are recorded by wrapping the instance's loss_function (the source is not edited)."""
+    mod = load_reference("nd_BSPDE_case.py")
+    D, M, N, Mm = 8, 12, 50, 2.2
+    layers = [D + 1, 64, 64, 1]
+    torch.manual_seed(TORCH_SEED)
+    np.random.seed(NUMPY_SEED)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = mod.CallOption(make_xi("ones", D), 1.0, M, N, D, Mm, layers, "FC", "Sine")
+        names = [k for k, _ in model.model.named_parameters()]
+        psum, pabs = param_checksums(model.model)
+        model.iteration, model.training_loss = [3996], [0.0]
+        trace, Ns = [], []
+        orig = model.loss_function
+
+        def spy(t, W, Xi):
+            res = orig(t, W, Xi)
+            trace.append(float(res[0].detach()))
+            Ns.append(int(W.shape[1] - 1))
+            return res
+
+        model.loss_function = spy
+        graph, min_loss, min_state = model.train(8, 1e-3)
+    last = names[-2]
+    np.savez_compressed(
+        os.path.join(OUT, "nd_schedule_trace.npz"), graph=np.asarray(graph, dtype=np.float64), trace_loss=np.array(trace),
+        trace_N=np.array(Ns), min_loss=np.float64(min_loss), min_X=min_state[0].numpy(), min_Y=min_state[1].numpy(),
+        param_names=np.array(names), param_sum=psum, param_abssum=pabs,
+        **{"final::" + last: dict(model.model.named_parameters())[last].detach().numpy().copy()},
+        meta=np.array(json.dumps(dict(torch_seed=TORCH_SEED, numpy_seed=NUMPY_SEED, D=D, M=M, N=N, Mm=Mm, layers=layers,
+                                      start_it=3996, K=8, lr=1e-3))))
+    print("nd_schedule_trace N per iteration", Ns, "losses", [f"{x:.5e}" for x in trace], "min", min_loss)
+
+
+def run_k30_case():
+    """BSB-100D, M = 100 (the shipped configuration): loss / Y0 trajectories over K = 30 Adam iterations, the horizon
+    SURVEY section 8(c) states its tolerance bars for."""
+    mod = load_reference("DeepBSDE.py")
+    D, M, N, K = 100, 100, 50, 30
+    torch.manual_seed(TORCH_SEED)
+    np.random.seed(NUMPY_SEED)
+    model = mod.BlackScholesBarenblatt(make_xi("bsb", D), 1.0, M, N, D, [D + 1] + 4 * [256] + [1], "FC", "Sine")
+    names = [k for k, _ in model.model.named_parameters()]
+    psum, pabs = param_checksums(model.model)
+    opt = torch.optim.Adam(model.model.parameters(), lr=1e-3)
+    tl, ty = [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(K):
+            opt.zero_grad()
+            t_b, W_b = model.fetch_minibatch()
+            loss, X, Y, Y0 = model.loss_function(t_b, W_b, model.Xi)
+            loss.backward()
+            opt.step()
+            tl.append(float(loss.detach()))
+            ty.append(float(Y0))
+    last = names[-2]
+    np.savez_compressed(
+        os.path.join(OUT, "bsb100_k30.npz"), trace_loss=np.array(tl), trace_Y0=np.array(ty), param_names=np.array(names),
+        param_sum=psum, param_abssum=pabs,
+        **{"final::" + last: dict(model.model.named_parameters())[last].detach().numpy().copy()},
+        meta=np.array(json.dumps(dict(torch_seed=TORCH_SEED, numpy_seed=NUMPY_SEED, D=D, M=M, N=N, K=K, lr=1e-3))))
+    print("bsb100_k30 loss[0], loss[-1], Y0[-1]:", tl[0], tl[-1], ty[-1])
+
+
+def run_comparator_case():
+    """The two closed-form comparators of the drivers on a fixed random prediction tensor."""
+    nd = load_reference("nd_BSPDE_case.py")
+    wc = load_reference("with_corr_high_dimension_pde.py")
+    rng = np.random.RandomState(7)
+    B, NT, A = 6, 11, 9
+    S = (0.6 + 0.8 * rng.rand(B, NT, A)).astype(np.float32)
+    t = np.tile(np.linspace(0.0, 1.0, NT, dtype=np.float32)[None, :, None], (B, 1, 1))
+    t[:, -1, :] = 0.95                                      # keep tau > 0 (tau = 0 with S == K is 0/0 upstream)
+    price, delta = nd.BasketOptionPriceCalculator.calculate_option_prices(torch.from_numpy(S), torch.from_numpy(t), 1.0,
+                                                                          0.05, 0.2, 1.0)
+    Xavg = 0.7 + 0.6 * rng.rand(5, NT)
+    Xavg[0, 3] = 1.0
+    times = np.linspace(0.0, 1.0, NT)
+    p2, d2 = wc.BasicOptionPriceCalculator().calculate_call_option_prices(Xavg, times, 1.0, 0.05, 0.2, 1.0, 25)
+    np.savez_compressed(os.path.join(OUT, "comparators.npz"), S=S, t=t, nd_price=price.numpy(), nd_delta=delta.numpy(),
+                        Xavg=Xavg, times=times, basic_price=p2, basic_delta=d2,
+                        cfg=np.array(json.dumps(dict(K=1.0, r=0.05, sigma=0.2, T=1.0, dims=25))))
+    print("comparators: nd price mean", float(price.mean()), "basic price mean", float(p2.mean()))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("make_golden.py needs /root/reference (build container only)")
@@ -266,3 +354,9 @@ if __name__ == "__main__":
         run_mc_cases()
     if not only or "basket_pricer" in only:
         run_basket_pricer_case()
+    if not only or "schedule" in only:
+        run_schedule_case()
+    if not only or "k30" in only:
+        run_k30_case()
+    if not only or "comparators" in only:
+        run_comparator_case()

@@ -18,9 +18,13 @@ def solver_cases():
     names = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         n = os.path.basename(f)[:-4]
-        if n not in ("mc_pricer", "bsb100_train_api", "basket_pricer"):
+        if n not in ("mc_pricer", "bsb100_train_api", "basket_pricer", "nd_schedule_trace", "bsb100_k30", "comparators"):
             names.append(n)
     return names
+
+
+def path(name):
+    return os.path.join(GOLDEN_DIR, name + ".npz")
 
 
 def load(name):

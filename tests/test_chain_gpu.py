@@ -16,13 +16,17 @@ from tests import golden_util as gu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def chain_forced():
+@pytest.fixture(params=["pair", "single"])
+def chain_forced(request):
+    """Chained dispatch forced on; "pair" = the cta_group::2 kernel where the shape allows it (3xTF32, widths multiples of
+    64), "single" = the single-CTA chain kernel everywhere."""
     import dnnpde_b200 as pde
     lib = pde._lib.load()
     old = lib.fbsnn_set_option(b"chain", 2)
+    old_pair = lib.fbsnn_set_option(b"chain_pair", 1 if request.param == "pair" else 0)
     yield lib
     lib.fbsnn_set_option(b"chain", old)
+    lib.fbsnn_set_option(b"chain_pair", old_pair)
 
 
 def _grads(sol):
@@ -44,6 +48,8 @@ SHAPES = [
     # D, M, N, layers, act, problem
     (100, 40, 50, [101, 256, 256, 256, 256, 1], "Sine", "bsb"),      # the benchmarked network, ragged last tile
     (100, 3, 50, [101, 256, 256, 256, 256, 1], "Sine", "bsb"),       # two tiles
+    (100, 700, 50, [101, 256, 256, 256, 256, 1], "Sine", "bsb"),     # 279 tiles: several tiles per CTA (pair: 140 pairs of 74)
+    (126, 90, 30, [127, 128, 192, 64, 1], "Tanh", "bsb"),            # pair-eligible mixed widths, 22 tiles
     (10, 300, 7, [11, 64, 128, 64, 1], "Tanh", "bsb"),               # ldx = 32, mixed widths
     (20, 77, 12, [21, 96, 96, 1], "ReLU", "hjb"),                    # two layers, odd chunk counts, |Z|^2 driver
     (6, 50, 9, [7, 128, 1], "Sine", "bsb"),                          # one hidden layer: no B sweep

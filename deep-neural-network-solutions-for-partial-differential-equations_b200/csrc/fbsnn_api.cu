@@ -530,7 +530,7 @@ static int g_opt_chain_pair = -1;
 static int chain_pair_mode() {
   if (g_opt_chain_pair < 0) {
     const char* e = getenv("FBSNN_CHAIN_PAIR");
-    g_opt_chain_pair = (e && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : 1;
+    g_opt_chain_pair = (e && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : 0;
   }
   return g_opt_chain_pair;
 }
@@ -539,6 +539,27 @@ static bool chain_use_pair(const Plan& p) {
   for (int l = 1; l <= p.L; ++l)
     if (p.H[l] % 64) return false;
   return true;
+}
+// CTAs per cluster that share (TMA-multicast) every weight k-block in the single-CTA chain kernel.  Option
+// "chain_cluster": 1, 2 or 4 (default 2); reduced until every MMA width splits into whole 8-row swizzle atoms per CTA.
+static int g_opt_chain_cluster = -1;
+static int chain_cluster_mode() {
+  if (g_opt_chain_cluster < 0) {
+    const char* e = getenv("FBSNN_CHAIN_CLUSTER");
+    g_opt_chain_cluster = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 1;
+  }
+  return g_opt_chain_cluster;
+}
+static int chain_cluster(const Plan& p) {
+  int cl = chain_cluster_mode();
+  auto fits = [&](int c) {
+    if (p.ldx % (8 * c)) return false;
+    for (int l = 1; l <= p.L; ++l)
+      if (p.H[l] % (8 * c)) return false;
+    return num_sms() % c == 0;
+  };
+  while (cl > 1 && !fits(cl)) cl >>= 1;
+  return cl;
 }
 static bool row_map(CUtensorMap* m, const float* base, int width, long long rows) {
   return tc::make_map(m, base, width, rows, width, 32, 128, false);
@@ -549,7 +570,7 @@ static bool weight_maps(const Plan& p, const Net& n, float* ws, int l, bool b_mn
   const int Hl = p.H[l];
   const float* hi = p.x3 ? ws + p.Whi[l] : n.W[l];
   const float* lo = p.x3 ? ws + p.Wlo[l] : n.W[l];
-  const int box_n = chain_use_pair(p) ? Hl / 2 : Hl;   // pair: each CTA loads half of the N rows of W^T
+  const int box_n = chain_use_pair(p) ? Hl / 2 : Hl / chain_cluster(p);   // each CTA of a pair / cluster loads its share of the N rows of W^T
   bool ok;
   if (!b_mn) {   // out = A[rows x K] * W^T: B[n = H_l][k]
     ok = tc::make_map(&m.whi[i], hi, K, Hl, K, 32, box_n, false) && tc::make_map(&m.wlo[i], lo, K, Hl, K, 32, box_n, false);
@@ -586,8 +607,9 @@ static int chain_launch(const FbsnnSpec* s, const Plan& p, const chain::Maps& m,
     a.ntiles = (int)((p.rows + 255) / 256);   // 256-row tiles, one per CTA pair
     e = chain::launch_chain2<SWEEP>(m, a, num_sms(), st);
   } else {
-    e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chain<SWEEP, true>(m, a, num_sms(), st)
-                                          : chain::launch_chain<SWEEP, false>(m, a, num_sms(), st);
+    const int cl = chain_cluster(p);
+    e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chain<SWEEP, true>(m, a, num_sms(), st, cl)
+                                          : chain::launch_chain<SWEEP, false>(m, a, num_sms(), st, cl);
   }
   if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
   if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "chained sweep %s: %s", what, cudaGetErrorString(e));
@@ -699,7 +721,8 @@ static int chain_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     if (rc) return rc;
     fin.job[fin.njobs++] = chain::ColFinJob{L, 0, p.H[L], grads + s->off_b[L]};
     fin.job[fin.njobs++] = chain::ColFinJob{L, 1, p.H[L], grads + s->off_W[L + 1]};
-    fin.nblk = chain_use_pair(p) ? chain::chain2_grid((int)((p.rows + 255) / 256), num_sms()) : std::min(a.ntiles, num_sms());
+    fin.nblk = chain_use_pair(p) ? chain::chain2_grid((int)((p.rows + 255) / 256), num_sms())
+                                 : chain::chain_grid((int)((p.rows + 127) / 128), num_sms(), chain_cluster(p));
   }
   if (L >= 2) {
     chain::Maps m;
@@ -1095,6 +1118,12 @@ int fbsnn_set_option(const char* name, int value) {
     const int old = chain_mode();
     if (value < 0 || value > 2) return fail(FBSNN_E_BADARG, "option chain takes 0, 1 or 2");
     g_opt_chain = value;
+    return old;
+  }
+  if (name && !strcmp(name, "chain_cluster")) {
+    const int old = chain_cluster_mode();
+    if (value != 1 && value != 2 && value != 4) return fail(FBSNN_E_BADARG, "option chain_cluster takes 1, 2 or 4");
+    g_opt_chain_cluster = value;
     return old;
   }
   if (name && !strcmp(name, "chain_pair")) {

@@ -259,11 +259,32 @@ __device__ __forceinline__ void chunk_colsum(const Args& a, const LinkD& L, int 
 // ----------------------------------------------------------------------------------------------------------------
 // single-CTA kernel
 // ----------------------------------------------------------------------------------------------------------------
-template <int SWEEP, bool X3>
+// CL = CTAs per cluster that SHARE every weight k-block: the CTAs of a cluster work on different row tiles but walk the
+// same sequence of weight k-blocks, so each one fetches 1/CL of a k-block and TMA-multicasts it into the shared memory of
+// all of them.  The sweeps are bound by the L2 -> SM fabric (about 10 TB/s over the chip), and with one CTA per k-block
+// fetch the weights are half of that traffic (every 128-row tile re-reads the 512 KB hi / lo twins of a layer).  A stage
+// of the weight ring is refilled once ALL CTAs' MMAs have released it (their commits are multicast to every CTA's
+// w_empty); nothing else couples the CTAs.  Every CTA runs the same number of tiles (tiles past the end are all padding).
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
+template <int SWEEP, bool X3, int CL>
 __global__ void __launch_bounds__(Cfg<X3>::NUM_THREADS, 1)
 chain_kernel(const __grid_constant__ Maps tm, const Args a) {
   using C = Cfg<X3>;
   constexpr int AS = C::A_STAGES, WS = C::W_STAGES;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+  const uint32_t crank = CL > 1 ? tc2::cluster_ctarank() : 0u;
+  const int tile_end = (int)blockIdx.x + ((a.ntiles + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x;   // same trip count in every CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* wring = smem;
@@ -295,7 +316,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
         if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.wlo[i]) : "memory");
       }
     }
-    for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], CL);
     for (int i = 0; i < AS; ++i) tc::mbar_init(&in_full[i], 1), tc::mbar_init(&a_ready[i], EW), tc::mbar_init(&a_free[i], 2);
     for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -305,7 +326,8 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) tc2::cluster_sync_all();   // every CTA's barriers are live before a peer's multicast can land on them
+  else __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   tc::pdl_trigger();
@@ -315,7 +337,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     // ===================== weight producer =====================
     if (lane == 0) {
       uint32_t ws = 0, wph = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int i = 0; i < a.nlinks; ++i) {
           const LinkD& L = a.link[i];
           if (!L.feeds) continue;
@@ -327,13 +349,22 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
             if (a.ablate & 16) {
               tc::mbar_arrive(&w_full[ws]);
             } else {
-              tc::mbar_expect_tx(&w_full[ws], bytes);
-              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
-                for (int c = 0; c < N / 32; ++c) {
-                  tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
-                  if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
+              tc::mbar_expect_tx(&w_full[ws], bytes);      // the whole k-block: this CTA's share + what the peers multicast in
+              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms; boxes dealt round-robin
+                for (int c = (int)crank; c < N / 32; c += CL) {
+                  if (CL > 1) {
+                    tma_load_2d_mc(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j, CMASK);
+                    if (X3) tma_load_2d_mc(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j, CMASK);
+                  } else {
+                    tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
+                    if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
+                  }
                 }
-              } else {        // W[n][k] (k contiguous): one N x 32 box
+              } else if (CL > 1) {   // W[n][k] (k contiguous): rows [crank * N / CL, ...) of the N x 32 box
+                const int ns = N / CL;
+                tma_load_2d_mc(dst + (int)crank * ns * 128, &tm.whi[i], &w_full[ws], 32 * j, (int)crank * ns, CMASK);
+                if (X3) tma_load_2d_mc(dst + 32768 + (int)crank * ns * 128, &tm.wlo[i], &w_full[ws], 32 * j, (int)crank * ns, CMASK);
+              } else {
                 tc::tma_load_2d(dst, &tm.whi[i], &w_full[ws], 32 * j, 0);
                 if (X3) tc::tma_load_2d(dst + 32768, &tm.wlo[i], &w_full[ws], 32 * j, 0);
               }
@@ -358,7 +389,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
         pf.next(a, (int)gridDim.x);
       };
       for (int p = 0; p < AS + 2; ++p) prefetch_one();
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int m0 = tile * 128;
         for (int i = 0; i < a.nlinks; ++i) {
           const LinkD& L = a.link[i];
@@ -384,7 +415,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0, ws = 0, wph = 0, mm = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int i = 0; i < a.nlinks; ++i) {
           const LinkD& L = a.link[i];
           const int nch = L.width >> 5;
@@ -421,7 +452,8 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
                   }
                 }
               }
-              tc::umma_commit(&w_empty[ws]);
+              if (CL > 1) umma_commit_mc(&w_empty[ws], CMASK);
+              else tc::umma_commit(&w_empty[ws]);
               if (++ws == WS) ws = 0, wph ^= 1;
             }
             tc::umma_commit(&a_free[s]);   // (also for chunks nothing reads: commits complete in order)
@@ -438,7 +470,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     // ===================== store warp =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int m0 = tile * 128;
         for (int i = 0; i < a.nlinks; ++i) {
           const LinkD& L = a.link[i];
@@ -468,7 +500,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     const int rt = q * 32 + lane;    // row inside the tile
     uint32_t s = 0, ph = 0, mmr = 0;
     bool first_tile = true;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, first_tile = false) {
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, first_tile = false) {
       const int row = tile * 128 + rt;
       const bool valid = row < a.rows;
       float yb = 0.f, yacc = 0.f;
@@ -524,7 +556,8 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     }
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) tc2::cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -870,10 +903,16 @@ __global__ void chain_colsum_finish_kernel(const float* __restrict__ colacc, con
   j.out[c] = (float)acc;
 }
 
-template <int SWEEP, bool X3>
-inline cudaError_t launch_chain(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {
+// grid of a launch with clusters of `cl` CTAs: a multiple of cl, at most the SM count, every CTA with >= 1 tile slot
+inline int chain_grid(int ntiles, int num_sms, int cl) {
+  const int cap = num_sms / cl * cl;
+  const int want = (ntiles + cl - 1) / cl * cl;
+  return want < cap ? want : cap;
+}
+template <int SWEEP, bool X3, int CL>
+inline cudaError_t launch_chain_cl(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {
   using C = Cfg<X3>;
-  auto kern = chain_kernel<SWEEP, X3>;
+  auto kern = chain_kernel<SWEEP, X3, CL>;
   static unsigned long long attr_devs = 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
@@ -882,10 +921,14 @@ inline cudaError_t launch_chain(const Maps& m, const Args& a, int num_sms, cudaS
     if (e != cudaSuccess) return e;
     attr_devs |= 1ull << dev;
   }
-  const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;
-  return tc::launch_pdl(kern, grid, C::NUM_THREADS, C::SMEM_BYTES, st, 1, m, a);
+  return tc::launch_pdl(kern, chain_grid(a.ntiles, num_sms, CL), C::NUM_THREADS, C::SMEM_BYTES, st, CL, m, a);
 }
-
+template <int SWEEP, bool X3>
+inline cudaError_t launch_chain(const Maps& m, const Args& a, int num_sms, cudaStream_t st, int cl = 1) {
+  if (cl == 4) return launch_chain_cl<SWEEP, X3, 4>(m, a, num_sms, st);
+  if (cl == 2) return launch_chain_cl<SWEEP, X3, 2>(m, a, num_sms, st);
+  return launch_chain_cl<SWEEP, X3, 1>(m, a, num_sms, st);
+}
 // CTA-pair launch: a.ntiles = number of 256-row tiles; grid = 2 x min(tiles, SMs / 2), cluster (2,1,1)
 template <int SWEEP>
 inline cudaError_t launch_chain2(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {

@@ -112,12 +112,16 @@ def test_reference_n_schedule_crossing_4000(cuda_graph):
     g = np.load(gu.path("nd_schedule_trace"), allow_pickle=False)
     meta = json.loads(str(g["meta"]))
     Dn, M = meta["D"], meta["M"]
+    # the fixture's network was initialised on the CPU generator (on a CUDA device both the reference and this class draw
+    # xavier_uniform_ from the CUDA generator): build the same class on the CPU under the fixture's seed for the weights
     torch.manual_seed(meta["torch_seed"])
+    cpu = pde.CallOptionND(np.ones((1, Dn)), 1.0, M, meta["N"], Dn, meta["Mm"], meta["layers"], "FC", "Sine", device="cpu")
+    psum = np.array([float(p.detach().double().sum()) for _, p in cpu.model.named_parameters()])
+    assert np.allclose(psum, g["param_sum"], rtol=0, atol=1e-9), "initial weights differ from the reference's"
     np.random.seed(meta["numpy_seed"])
     sol = pde.CallOptionND(np.ones((1, Dn)), 1.0, M, meta["N"], Dn, meta["Mm"], meta["layers"], "FC", "Sine",
                            precision="fp32", n_schedule="reference", cuda_graph=cuda_graph)
-    psum = np.array([float(p.detach().double().sum()) for _, p in sol.model.named_parameters()])
-    assert np.allclose(psum, g["param_sum"], rtol=0, atol=1e-9), "initial weights differ from the reference's"
+    sol.model.load_state_dict(cpu.model.state_dict())
     sol.iteration, sol.training_loss = [meta["start_it"]], [0.0]
     graph, min_loss, min_state = sol.train(meta["K"], meta["lr"])
     tl = sol.last_losses.astype(np.float64)

@@ -38,11 +38,13 @@ def main():
     ap.add_argument("--act", default="Sine")
     ap.add_argument("--problem", default="bsb")
     ap.add_argument("--fwd-only", action="store_true")
-    ap.add_argument("--pair", type=int, default=1, help="chain_pair option (cta_group::2 chain kernel when eligible)")
+    ap.add_argument("--pair", type=int, default=0, help="chain_pair option (cta_group::2 chain kernel when eligible)")
+    ap.add_argument("--cluster", type=int, default=2, help="chain_cluster option (CTAs sharing a weight k-block)")
     args = ap.parse_args()
     import dnnpde_b200 as pde
     lib = pde._lib.load()
     lib.fbsnn_set_option(b"chain_pair", args.pair)
+    lib.fbsnn_set_option(b"chain_cluster", args.cluster)
     D, M, N = args.dim, args.paths, args.steps
     layers = [int(x) for x in args.layers.split(",")] if args.layers else [D + 1] + 4 * [256] + [1]
     torch.manual_seed(1)

@@ -33,11 +33,41 @@ def run(collective, data_parallel, M, K, precision):
     return sol._fp.flat.detach().clone(), np.array(sol.last_losses), sol.collective
 
 
+def run_philox(data_parallel, M, K1, K2, cuda_graph=True):
+    """Two consecutive train() calls with in-kernel increments (brownian='philox'): -> per-iteration losses of both."""
+    D, N = 100, 20
+    layers = [D + 1, 256, 256, 256, 256, 1]
+    torch.manual_seed(3)
+    Xi = np.array([1.0, 0.5] * (D // 2))[None, :]
+    sol = pde.BlackScholesBarenblatt(Xi, 1.0, M, N, D, layers, "FC", "Sine", precision="fp32", brownian="philox", seed=41,
+                                     data_parallel=data_parallel, collective="peer", cuda_graph=cuda_graph)
+    sol.train(K1, 1e-3)
+    l1 = np.array(sol.last_losses)
+    sol.train(K2, 1e-3)
+    l2 = np.array(sol.last_losses)
+    torch.cuda.synchronize()
+    return l1, l2, sol._fp.flat.detach().clone()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
+    # ---- in-kernel increments on several GPUs: the persistent device counter keys Philox (ADVICE r1) -------------
+    a1, a2, pa = run_philox(True, 203, 4, 4, cuda_graph=True)       # data-parallel, graph-captured peer step
+    e1, e2, pe = run_philox(True, 203, 4, 4, cuda_graph=False)      # data-parallel, eager
+    fresh = not np.allclose(a1, a2, rtol=1e-3)                       # second train() call draws NEW noise
+    graph_eq = bool(np.allclose(a1, e1, rtol=1e-6) and np.allclose(a2, e2, rtol=1e-6) and
+                    float((pa - pe).abs().max()) <= 1e-6)
+    msg = f"[philox] second train() draws fresh noise={fresh} graph==eager={graph_eq}"
+    ok &= fresh and graph_eq
+    if rank == 0:
+        s1, s2, _ = run_philox(False, 203, 4, 4)                     # the same two calls on ONE GPU
+        rl = float(max(np.max(np.abs(a1 - s1) / np.abs(s1)), np.max(np.abs(a2 - s2) / np.abs(s2))))
+        msg += f" max rel loss diff vs 1 GPU={rl:.3e}"
+        ok &= rl <= 2e-4
+        print(msg, flush=True)
     for precision, tol in (("fp32", 2e-5), ("tf32x3", 5e-5)):
         M, K = 203, 6                        # uneven shards
         p_peer, l_peer, used = run("peer", True, M, K, precision)

@@ -534,32 +534,30 @@ static int chain_pair_mode() {
   }
   return g_opt_chain_pair;
 }
-static bool chain_use_pair(const Plan& p) {
-  if (!p.x3 || chain_pair_mode() == 0 || p.ldx % 64) return false;
+// Operand of the next MMA in tensor memory (chaint_kernel).  Option "chain_ta" / FBSNN_CHAIN_TA: 1 (default) = on, 0 = the
+// shared-memory forms above.
+static int g_opt_chain_ta = -1;
+static int chain_ta_mode() {
+  if (g_opt_chain_ta < 0) {
+    const char* e = getenv("FBSNN_CHAIN_TA");
+    g_opt_chain_ta = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_opt_chain_ta;
+}
+// chaint_kernel deals the chunks of every link alternately to its two half-teams and ties ring stages to them: every width
+// has to be an even number of 32-column chunks (else the shared-memory chain kernel runs)
+static bool chain_use_ta(const Plan& p) {
+  if (!chain_ta_mode() || p.ldx % 64) return false;
   for (int l = 1; l <= p.L; ++l)
     if (p.H[l] % 64) return false;
   return true;
 }
-// CTAs per cluster that share (TMA-multicast) every weight k-block in the single-CTA chain kernel.  Option
-// "chain_cluster": 1, 2 or 4 (default 2); reduced until every MMA width splits into whole 8-row swizzle atoms per CTA.
-static int g_opt_chain_cluster = -1;
-static int chain_cluster_mode() {
-  if (g_opt_chain_cluster < 0) {
-    const char* e = getenv("FBSNN_CHAIN_CLUSTER");
-    g_opt_chain_cluster = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 1;
-  }
-  return g_opt_chain_cluster;
-}
-static int chain_cluster(const Plan& p) {
-  int cl = chain_cluster_mode();
-  auto fits = [&](int c) {
-    if (p.ldx % (8 * c)) return false;
-    for (int l = 1; l <= p.L; ++l)
-      if (p.H[l] % (8 * c)) return false;
-    return num_sms() % c == 0;
-  };
-  while (cl > 1 && !fits(cl)) cl >>= 1;
-  return cl;
+static bool chain_use_pair(const Plan& p) {
+  if (chain_use_ta(p)) return false;
+  if (!p.x3 || chain_pair_mode() == 0 || p.ldx % 64) return false;
+  for (int l = 1; l <= p.L; ++l)
+    if (p.H[l] % 64) return false;
+  return true;
 }
 static bool row_map(CUtensorMap* m, const float* base, int width, long long rows) {
   return tc::make_map(m, base, width, rows, width, 32, 128, false);
@@ -570,7 +568,7 @@ static bool weight_maps(const Plan& p, const Net& n, float* ws, int l, bool b_mn
   const int Hl = p.H[l];
   const float* hi = p.x3 ? ws + p.Whi[l] : n.W[l];
   const float* lo = p.x3 ? ws + p.Wlo[l] : n.W[l];
-  const int box_n = chain_use_pair(p) ? Hl / 2 : Hl / chain_cluster(p);   // each CTA of a pair / cluster loads its share of the N rows of W^T
+  const int box_n = chain_use_pair(p) ? Hl / 2 : Hl;   // each CTA of a pair loads its half of the N rows of W^T
   bool ok;
   if (!b_mn) {   // out = A[rows x K] * W^T: B[n = H_l][k]
     ok = tc::make_map(&m.whi[i], hi, K, Hl, K, 32, box_n, false) && tc::make_map(&m.wlo[i], lo, K, Hl, K, 32, box_n, false);
@@ -603,13 +601,15 @@ static int chain_launch(const FbsnnSpec* s, const Plan& p, const chain::Maps& m,
   chain_timing_begin(slot, a, what, st);
   ++g_launches;
   cudaError_t e;
-  if (chain_use_pair(p)) {
+  if (chain_use_ta(p)) {
+    e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chaint<SWEEP, true>(m, a, num_sms(), st)
+                                          : chain::launch_chaint<SWEEP, false>(m, a, num_sms(), st);
+  } else if (chain_use_pair(p)) {
     a.ntiles = (int)((p.rows + 255) / 256);   // 256-row tiles, one per CTA pair
     e = chain::launch_chain2<SWEEP>(m, a, num_sms(), st);
   } else {
-    const int cl = chain_cluster(p);
-    e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chain<SWEEP, true>(m, a, num_sms(), st, cl)
-                                          : chain::launch_chain<SWEEP, false>(m, a, num_sms(), st, cl);
+    e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chain<SWEEP, true>(m, a, num_sms(), st)
+                                          : chain::launch_chain<SWEEP, false>(m, a, num_sms(), st);
   }
   if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
   if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "chained sweep %s: %s", what, cudaGetErrorString(e));
@@ -722,7 +722,7 @@ static int chain_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     fin.job[fin.njobs++] = chain::ColFinJob{L, 0, p.H[L], grads + s->off_b[L]};
     fin.job[fin.njobs++] = chain::ColFinJob{L, 1, p.H[L], grads + s->off_W[L + 1]};
     fin.nblk = chain_use_pair(p) ? chain::chain2_grid((int)((p.rows + 255) / 256), num_sms())
-                                 : chain::chain_grid((int)((p.rows + 127) / 128), num_sms(), chain_cluster(p));
+                                 : chain::chain_grid((int)((p.rows + 127) / 128), num_sms());
   }
   if (L >= 2) {
     chain::Maps m;
@@ -1120,20 +1120,43 @@ int fbsnn_set_option(const char* name, int value) {
     g_opt_chain = value;
     return old;
   }
-  if (name && !strcmp(name, "chain_cluster")) {
-    const int old = chain_cluster_mode();
-    if (value != 1 && value != 2 && value != 4) return fail(FBSNN_E_BADARG, "option chain_cluster takes 1, 2 or 4");
-    g_opt_chain_cluster = value;
-    return old;
-  }
   if (name && !strcmp(name, "chain_pair")) {
     const int old = chain_pair_mode();
     if (value < 0 || value > 1) return fail(FBSNN_E_BADARG, "option chain_pair takes 0 or 1");
     g_opt_chain_pair = value;
     return old;
   }
+  if (name && !strcmp(name, "chain_ta")) {
+    const int old = chain_ta_mode();
+    if (value < 0 || value > 1) return fail(FBSNN_E_BADARG, "option chain_ta takes 0 or 1");
+    g_opt_chain_ta = value;
+    return old;
+  }
   return fail(FBSNN_E_BADARG, "unknown option %s", name ? name : "(null)");
 }
+#ifdef FBSNN_CHAIN_PROF
+// profiling builds only (tools/chain_prof.py): copies (and optionally clears) the 160 x 24 cycle counters of chaint_kernel
+extern "C" int fbsnn_debug_chain_prof(unsigned long long* out, int reset) {
+  if (out && cudaMemcpyFromSymbol(out, chain::g_chain_prof, sizeof(chain::g_chain_prof)) != cudaSuccess) return FBSNN_E_CUDA;
+  if (reset) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, chain::g_chain_prof) != cudaSuccess) return FBSNN_E_CUDA;
+    cudaMemset(p, 0, sizeof(chain::g_chain_prof));
+  }
+  return 0;
+}
+#endif
+#ifdef FBSNN_CHAIN_PROF
+extern "C" int fbsnn_debug_chain_trap(unsigned int* out8, int reset) {
+  if (out8 && cudaMemcpyFromSymbol(out8, chain::g_chain_trap, sizeof(chain::g_chain_trap)) != cudaSuccess) return FBSNN_E_CUDA;
+  if (reset) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, chain::g_chain_trap) != cudaSuccess) return FBSNN_E_CUDA;
+    cudaMemset(p, 0, sizeof(chain::g_chain_trap));
+  }
+  return 0;
+}
+#endif
 long long fbsnn_launch_count(void) { return g_launches; }
 void fbsnn_dense_timing(int enable) { g_timing = enable != 0; g_ntimed = 0; }
 // Sums the recorded dense-layer launches (caller has synchronised): out = {n_launches, total ms, total FLOPs,

@@ -153,12 +153,14 @@ struct ChunkIt {
 // CW = columns of the chunk this thread handles, starting at column u0 * 4 of the chunk (v[] = its accumulator fragment).
 // (i0, i2) = where the loaded input chunks are: the output buffers themselves (in-place, single-CTA kernel) or a separate
 // input ring (CTA-pair kernel; pass-through links then have to copy their operand into buf0).
-template <int SWEEP, bool X3, int CW, bool INPLACE>
+// TA = the operand of the next MMA goes to TENSOR MEMORY (chaint_kernel): its values come back in hi_out[] instead of
+// buf0 / buf1, and shared memory is written only for what a TMA store or a column sum reads.
+template <int SWEEP, bool X3, int CW, bool INPLACE, bool TA = false>
 __device__ __forceinline__ void chunk_math(const Args& a, const LinkD& L, int i, int c0, int rt, int u0, const float* i0,
-                                           const float* i2, float* b0, float* b1, float* b2, const uint32_t (&v)[CW],
-                                           float yb, float& yacc) {
+                                           const float* i2, float* b0, float* b1, float* b2, const uint32_t* v,
+                                           float yb, float& yacc, uint32_t* hi_out = nullptr) {
   const int rsw = rt & 7;
-  const bool want_lo = X3 && L.feeds;
+  const bool want_lo = X3 && L.feeds && !TA;
 #pragma unroll
   for (int uu = 0; uu < CW / 4; ++uu) {
     const int u = u0 + uu;
@@ -232,6 +234,12 @@ __device__ __forceinline__ void chunk_math(const Args& a, const LinkD& L, int i,
         for (int t = 0; t < 4; ++t) o0[t] = ac[t] * x0[t] + x2[t];
       }
     }
+    if constexpr (TA) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) hi_out[4 * uu + t] = __float_as_uint(o0[t]);
+      w0 = L.out0 || (L.colsum & 1);
+      w2 = w2 && (L.out2 || (L.colsum & 2));
+    }
     if (w0) st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
     if (want_lo) st4(b1 + off, make_float4(lo_part(o0[0]), lo_part(o0[1]), lo_part(o0[2]), lo_part(o0[3])));
     if (w2) st4(b2 + off, make_float4(o2[0], o2[1], o2[2], o2[3]));
@@ -252,39 +260,21 @@ __device__ __forceinline__ void chunk_colsum(const Args& a, const LinkD& L, int 
     if (L.colsum & 2) s2 += b2[idx];
   }
   float* dst = a.colacc + ((size_t)(blockIdx.x * kMaxLinks + i) * 2) * 1024 + q * 256 + c0 + lane;
-  if (L.colsum & 1) dst[0] = first_tile ? s0 : dst[0] + s0;
-  if (L.colsum & 2) dst[1024] = first_tile ? s2 : dst[1024] + s2;
+  // the owner's store and its later REDs to the same address are applied in program order: deterministic, and the
+  // L2 round trip of a read-modify-write stays off the chunk's critical path
+  if (L.colsum & 1) { if (first_tile) dst[0] = s0; else atomicAdd(dst, s0); }
+  if (L.colsum & 2) { if (first_tile) dst[1024] = s2; else atomicAdd(dst + 1024, s2); }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
 // single-CTA kernel
 // ----------------------------------------------------------------------------------------------------------------
-// CL = CTAs per cluster that SHARE every weight k-block: the CTAs of a cluster work on different row tiles but walk the
-// same sequence of weight k-blocks, so each one fetches 1/CL of a k-block and TMA-multicasts it into the shared memory of
-// all of them.  The sweeps are bound by the L2 -> SM fabric (about 10 TB/s over the chip), and with one CTA per k-block
-// fetch the weights are half of that traffic (every 128-row tile re-reads the 512 KB hi / lo twins of a layer).  A stage
-// of the weight ring is refilled once ALL CTAs' MMAs have released it (their commits are multicast to every CTA's
-// w_empty); nothing else couples the CTAs.  Every CTA runs the same number of tiles (tiles past the end are all padding).
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-
-template <int SWEEP, bool X3, int CL>
+template <int SWEEP, bool X3>
 __global__ void __launch_bounds__(Cfg<X3>::NUM_THREADS, 1)
 chain_kernel(const __grid_constant__ Maps tm, const Args a) {
   using C = Cfg<X3>;
   constexpr int AS = C::A_STAGES, WS = C::W_STAGES;
-  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
-  const uint32_t crank = CL > 1 ? tc2::cluster_ctarank() : 0u;
-  const int tile_end = (int)blockIdx.x + ((a.ntiles + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x;   // same trip count in every CTA
+  const int tile_end = a.ntiles;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* wring = smem;
@@ -316,7 +306,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
         if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.wlo[i]) : "memory");
       }
     }
-    for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], CL);
+    for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
     for (int i = 0; i < AS; ++i) tc::mbar_init(&in_full[i], 1), tc::mbar_init(&a_ready[i], EW), tc::mbar_init(&a_free[i], 2);
     for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -326,8 +316,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc::tc_fence_before();
-  if (CL > 1) tc2::cluster_sync_all();   // every CTA's barriers are live before a peer's multicast can land on them
-  else __syncthreads();
+  __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   tc::pdl_trigger();
@@ -349,22 +338,13 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
             if (a.ablate & 16) {
               tc::mbar_arrive(&w_full[ws]);
             } else {
-              tc::mbar_expect_tx(&w_full[ws], bytes);      // the whole k-block: this CTA's share + what the peers multicast in
-              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms; boxes dealt round-robin
-                for (int c = (int)crank; c < N / 32; c += CL) {
-                  if (CL > 1) {
-                    tma_load_2d_mc(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j, CMASK);
-                    if (X3) tma_load_2d_mc(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j, CMASK);
-                  } else {
-                    tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
-                    if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
-                  }
+              tc::mbar_expect_tx(&w_full[ws], bytes);
+              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
+                for (int c = 0; c < N / 32; ++c) {
+                  tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
+                  if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
                 }
-              } else if (CL > 1) {   // W[n][k] (k contiguous): rows [crank * N / CL, ...) of the N x 32 box
-                const int ns = N / CL;
-                tma_load_2d_mc(dst + (int)crank * ns * 128, &tm.whi[i], &w_full[ws], 32 * j, (int)crank * ns, CMASK);
-                if (X3) tma_load_2d_mc(dst + 32768 + (int)crank * ns * 128, &tm.wlo[i], &w_full[ws], 32 * j, (int)crank * ns, CMASK);
-              } else {
+              } else {        // W[n][k] (k contiguous): one N x 32 box
                 tc::tma_load_2d(dst, &tm.whi[i], &w_full[ws], 32 * j, 0);
                 if (X3) tc::tma_load_2d(dst + 32768, &tm.wlo[i], &w_full[ws], 32 * j, 0);
               }
@@ -452,8 +432,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
                   }
                 }
               }
-              if (CL > 1) umma_commit_mc(&w_empty[ws], CMASK);
-              else tc::umma_commit(&w_empty[ws]);
+              tc::umma_commit(&w_empty[ws]);
               if (++ws == WS) ws = 0, wph ^= 1;
             }
             tc::umma_commit(&a_free[s]);   // (also for chunks nothing reads: commits complete in order)
@@ -556,8 +535,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     }
   }
   tc::tc_fence_before();
-  if (CL > 1) tc2::cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -881,6 +859,634 @@ chain2_kernel(const __grid_constant__ Maps tm, const Args a) {
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// chaint_kernel: the carried operand lives in TENSOR MEMORY.
+//
+// In chain_kernel the chunk the epilogue writes is at once MMA operand, TMA-store source and the landing zone of the next
+// input load, so a stage is only re-loaded after the MMAs AND the store of its previous chunk -- with two 48 KB stages
+// next to 128 KB of weight twins the row-array traffic cannot overlap the MMAs (ablation table: A sweep 13.4 ms = 7.1 ms
+// without I/O + 6.3 ms of I/O at HBM speed).  Here
+//   * the epilogue team first DRAINS the whole accumulator (half into registers, half parked in 128 spare TMEM columns),
+//     which frees it for the next MMA at once: one 256-column accumulator suffices;
+//   * the last 128 TMEM columns are a ring of A-operand stages (hi in 32 columns, 3xTF32 lo in the next 32): the team
+//     writes the next layer's operand with tcgen05.st (lane = row, column = k) and the MMAs take A from TMEM
+//     (tcgen05.mma [d], [a], b_desc), so they read only the weight k-block from shared memory;
+//   * shared memory beside the weight ring is a pure I/O ring (3-4 stages of in0|in2 -> out0|out2, 32 KB each) that the
+//     MMAs never touch: a stage is free again as soon as its TMA store has read it, and loads run 3-4 chunks ahead.
+// Warps as chain_kernel: 0 weight producer | 1 MMA issuer | 2 input producer | 3 store | 4..19 epilogue team.
+// ----------------------------------------------------------------------------------------------------------------
+template <bool X3>
+struct CfgT {
+  static constexpr int W_STAGE = X3 ? 65536 : 32768;
+  static constexpr int W_STAGES = X3 ? 2 : 3;
+  static constexpr int IO_STAGE = 2 * CHUNK_BYTES;       // [buf0 = in0 / out0][buf2 = in2 / out2]
+  static constexpr int IO_STAGES = X3 ? 3 : 4;
+  // TMEM: accumulator [0, 256) | parked accumulator chunks [256, 384) | operand ring [384, 512)
+  static constexpr int PARK_COL = 256, TA_COL0 = 384;
+  static constexpr int TA_COLS = X3 ? 64 : 32;           // TMEM columns of one operand stage: hi (, lo)
+  static constexpr int TA_STAGES = 128 / TA_COLS;
+  static constexpr int EPI_WARPS = 16, CW = 16, EPI_WARP0 = 4;   // two half-teams of 8 warps, 16 columns of a chunk per thread
+  static constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+  static constexpr int EXTRA_BYTES = 2048;               // barriers (512 B), head partials (1536 B)
+  static constexpr int SMEM_BYTES = W_STAGES * W_STAGE + IO_STAGES * IO_STAGE + EXTRA_BYTES + 1024 /*align*/;
+};
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// ac[c] = (jq == jj) ? v[c] : ac[c]
+__device__ __forceinline__ void sel8(uint32_t (&ac)[8], const uint32_t* v, int jq, int jj) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %16, %17;\n\t"
+      "selp.b32 %0, %8, %0, p;\n\tselp.b32 %1, %9, %1, p;\n\tselp.b32 %2, %10, %2, p;\n\tselp.b32 %3, %11, %3, p;\n\t"
+      "selp.b32 %4, %12, %4, p;\n\tselp.b32 %5, %13, %5, p;\n\tselp.b32 %6, %14, %6, p;\n\tselp.b32 %7, %15, %7, p;\n\t}"
+      : "+r"(ac[0]), "+r"(ac[1]), "+r"(ac[2]), "+r"(ac[3]), "+r"(ac[4]), "+r"(ac[5]), "+r"(ac[6]), "+r"(ac[7])
+      : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(jq), "r"(jj));
+}
+// ac[k] = which ? v1[k] : v0[k]
+__device__ __forceinline__ void sel16(uint32_t (&ac)[16], const uint32_t (&v0)[16], const uint32_t (&v1)[16], int which) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.b32 %0, %2, %1, p;\n\t}" : "=r"(ac[k]) : "r"(v0[k]), "r"(v1[k]), "r"(which));
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// bounded wait without a function call: a call anywhere in the kernel (chain_timeout's printf) makes ptxas allocate
+// every setmaxnreg region for the smallest limit
+#ifdef FBSNN_CHAIN_PROF
+// debugging builds: the first wait that times out records who starved {block, role, what, link, chunk, parity} and turns
+// every later wait of the launch into a no-op, so that the kernel ends (with garbage) and the host can read the record
+__device__ unsigned int g_chain_trap[8];
+__device__ __forceinline__ void twait(uint64_t* b, uint32_t parity, int role, int what, int link, int chunk) {
+  uint32_t ok = 0, spins = 0;
+  const uint32_t addr = smem_u32(b);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (*(volatile unsigned int*)&g_chain_trap[0]) break;
+    if (++spins > (1u << 20)) {
+      if (atomicCAS(&g_chain_trap[0], 0u, 1u) == 0u) {
+        g_chain_trap[1] = blockIdx.x, g_chain_trap[2] = role, g_chain_trap[3] = what, g_chain_trap[4] = link;
+        g_chain_trap[5] = chunk, g_chain_trap[6] = parity, g_chain_trap[7] = threadIdx.x;
+        __threadfence();
+      }
+      break;
+    }
+  }
+}
+#else
+__device__ __forceinline__ void twait(uint64_t* b, uint32_t parity, int, int, int, int) {
+  uint32_t ok = 0, spins = 0;
+  const uint32_t addr = smem_u32(b);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > tc::kSpinLimit) asm volatile("trap;");
+  }
+}
+
+#endif
+// Wait / work cycle accounting of chaint_kernel (builds with -DFBSNN_CHAIN_PROF only: tools/chain_prof.py): every role
+// thread attributes the cycles since its previous lap to one slot of g_chain_prof[CTA][slot].
+#ifdef FBSNN_CHAIN_PROF
+__device__ unsigned long long g_chain_prof[4][160][24];   // [sweep][CTA][slot]
+#define CPROF_BEGIN(on) const bool _cpon = (on); long long _cp = clock64();
+#define CPROF_LAP(k)                                                                            \
+  if (_cpon) {                                                                                  \
+    const long long _n = clock64();                                                             \
+    atomicAdd(&g_chain_prof[SWEEP][blockIdx.x][k], (unsigned long long)(_n - _cp));                    \
+    _cp = _n;                                                                                   \
+  }
+#else
+#define CPROF_BEGIN(on)
+#define CPROF_LAP(k)
+#endif
+
+// Barriers and rings the epilogue threads of chaint_kernel work with, and a thread's position in them.
+struct TeamCtx {
+  uint64_t *in_full, *out_ready, *a_ready, *a_free, *acc_full, *acc_empty;
+  uint8_t* ioring;
+  float* ypart;
+  uint32_t lane_base;             // TMEM address of this warp's lane quarter
+  int q, h2, grp, rt, lane;
+  uint32_t* started;              // [2] per half-team: 1 + index of its latest chunk whose inputs it has seen land
+  uint32_t t, tph, s, sph, dr;    // I/O stage + phase, operand stage + phase, accumulators drained so far
+  uint32_t gc;                    // chunks of this launch so far (both half-teams count all of them)
+};
+
+// 16 columns (this thread's half of chunk j, row rt) of link `i`: straight-line code per (SWEEP, KIND, ACT) -- what the
+// generic chunk_math decides per 4-column group at run time (link kind, which buffers exist, activation) costs more
+// instructions than the arithmetic itself.  Same arithmetic, in the same order, as chunk_math.
+//   ac[]  accumulator slice, b0 / b2 = the I/O stage's buffers (inputs on entry, outputs on exit), hi[] = operand of the
+//   next MMA (KIND != LINK_LAST).
+template <int SWEEP, int KIND, int ACT>
+__device__ __forceinline__ void ta_math16(const Args& a, int i, int c0, int rt, int h2, float* b0, float* b2,
+                                          const uint32_t (&ac)[16], float yb, float& yacc, uint32_t (&hi)[16]) {
+  const int rsw = rt & 7;
+#pragma unroll
+  for (int uu = 0; uu < 4; ++uu) {
+    const int u = 4 * h2 + uu;
+    const int off = rt * 32 + ((u ^ rsw) << 2);
+    const int col = c0 + 4 * u;
+    const float acc[4] = {__uint_as_float(ac[4 * uu]), __uint_as_float(ac[4 * uu + 1]), __uint_as_float(ac[4 * uu + 2]),
+                          __uint_as_float(ac[4 * uu + 3])};
+    float o0[4];
+    if constexpr (KIND == LINK_FIRST && SWEEP != SWEEP_A) {          // X / V / zbar_L pass through
+      const float4 x = ld4(b0 + off);
+      o0[0] = x.x, o0[1] = x.y, o0[2] = x.z, o0[3] = x.w;
+    } else if constexpr (SWEEP == SWEEP_F) {                         // g = act(z), a = act'(z)
+      const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias[i] + col));
+      const float z[4] = {acc[0] + b.x, acc[1] + b.y, acc[2] + b.z, acc[3] + b.w};
+      float o2[4];
+      act_ga4(ACT, z, o0, o2);
+      st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+      st4(b2 + off, make_float4(o2[0], o2[1], o2[2], o2[3]));
+      if constexpr (KIND == LINK_LAST) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + col));
+        yacc = fmaf(o0[0], w.x, fmaf(o0[1], w.y, fmaf(o0[2], w.z, fmaf(o0[3], w.w, yacc))));
+      }
+    } else if constexpr (SWEEP == SWEEP_A) {
+      if constexpr (KIND == LINK_FIRST) {                            // delta_L = wout * a_L
+        const float4 x = ld4(b0 + off);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.wout + col));
+        o0[0] = w.x * x.x, o0[1] = w.y * x.y, o0[2] = w.z * x.z, o0[3] = w.w * x.w;
+        st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+      } else if constexpr (KIND == LINK_MID) {                       // ht = acc; delta = ht * a; s = ht * c(g, a)
+        const float4 x = ld4(b0 + off);
+        const float x0[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = acc[t] * x0[t];
+        if (a.with_s) {
+          const float4 g4 = ld4(b2 + off);
+          const float x2[4] = {g4.x, g4.y, g4.z, g4.w};
+          float o2[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o2[t] = acc[t] * act_c(ACT, x2[t], x0[t]);
+          st4(b2 + off, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        }
+        st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+      } else {                                                       // Du
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = acc[t];
+        st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+      }
+    } else if constexpr (SWEEP == SWEEP_T) {
+      const float4 x = ld4(b0 + off), y = ld4(b2 + off);
+      const float x0[4] = {x.x, x.y, x.z, x.w}, x2[4] = {y.x, y.y, y.z, y.w};
+      float o2[4];
+      if constexpr (KIND == LINK_MID) {                              // dbar = acc; hd = dbar * a; zz = dbar * s
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o0[t] = acc[t] * x0[t], o2[t] = acc[t] * x2[t];
+      } else {   // last hidden layer: zbar = ybar wout a + dbar (wout c);  wg = dbar a + ybar g  (column sums only)
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wout + col));
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float av = x0[t], gv = x2[t];
+          const float sv = w[t] * act_c(ACT, gv, av);
+          const float zz = acc[t] * sv;
+          o0[t] = zz + yb * w[t] * av;
+          o2[t] = acc[t] * av + yb * gv;
+        }
+      }
+      st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+      st4(b2 + off, make_float4(o2[0], o2[1], o2[2], o2[3]));
+    } else {                                                         // B: hb = acc; zbar = hb * a + zz
+      const float4 x = ld4(b0 + off), y = ld4(b2 + off);
+      o0[0] = acc[0] * x.x + y.x, o0[1] = acc[1] * x.y + y.y, o0[2] = acc[2] * x.z + y.z, o0[3] = acc[3] * x.w + y.w;
+      st4(b0 + off, make_float4(o0[0], o0[1], o0[2], o0[3]));
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) hi[4 * uu + t] = __float_as_uint(o0[t]);
+  }
+}
+
+// One link of one tile for an epilogue thread of chaint_kernel: drain the accumulator (KIND != LINK_FIRST), then this
+// half-team's chunks.  FEEDS / has-accumulator / column sums follow from (SWEEP, KIND) -- fbsnn_api.cu builds the links so.
+template <int SWEEP, int KIND, bool X3, int ACT>
+__device__ __forceinline__ void ta_link(const Args& a, const LinkD& L, int i, TeamCtx& c, float yb, float& yacc, bool first_tile) {
+  using C = CfgT<X3>;
+  constexpr int IOS = C::IO_STAGES, TS = C::TA_STAGES, EW = C::EPI_WARPS, CW = C::CW;
+  constexpr bool HAS_ACC = KIND != LINK_FIRST, FEEDS = KIND != LINK_LAST;
+  constexpr int COLSUM = (SWEEP == SWEEP_T && KIND == LINK_LAST) ? 3 : (SWEEP == SWEEP_B && KIND != LINK_FIRST) ? 1 : 0;
+  const int nch = L.width >> 5;
+  const int grp = c.grp, h2 = c.h2;
+  // This thread's slice of the accumulator: 16 columns of each of its (up to 4) chunks.  The chunks j < 4 stay in registers,
+  // the chunks j >= 4 are PARKED in TMEM columns [256, 384) -- 64 registers per thread would not fit next to the working
+  // set.  Each warp reads back only what it parked itself (same lanes, same columns).
+  // (Unconditional loads: columns past the link's width are stale accumulator columns nobody uses.)
+  uint32_t v0[16], v1[16];
+  CPROF_BEGIN(c.q == 0 && c.h2 == 0 && c.grp == 0 && c.lane == 0)
+  if constexpr (HAS_ACC) {
+    twait(&c.acc_full[0], c.dr & 1, 4, 0, i, 0);
+    CPROF_LAP(0)
+    tc::tc_fence_after();
+    if (nch > 4) {
+      uint32_t p0[16], p1[16];
+      tmem_ld16_nowait(c.lane_base + (uint32_t)(32 * (4 + grp) + h2 * CW), p0);
+      tmem_ld16_nowait(c.lane_base + (uint32_t)(32 * (6 + grp) + h2 * CW), p1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_st16(c.lane_base + (uint32_t)(C::PARK_COL + 32 * grp + h2 * CW), p0);
+      tmem_st16(c.lane_base + (uint32_t)(C::PARK_COL + 32 * (2 + grp) + h2 * CW), p1);
+    }
+    tmem_ld16_nowait(c.lane_base + (uint32_t)(32 * grp + h2 * CW), v0);
+    tmem_ld16_nowait(c.lane_base + (uint32_t)(32 * (2 + grp) + h2 * CW), v1);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc::tc_fence_before();
+    __syncwarp();
+    if (c.lane == 0) tc::mbar_arrive(&c.acc_empty[0]);
+    ++c.dr;
+    CPROF_LAP(1)
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v0[k] = 0u, v1[k] = 0u;
+  }
+#pragma unroll 1
+  for (int j = 0; j < nch; ++j) {
+    if ((j & 1) == grp) {
+      uint32_t ac[CW];
+      if (!HAS_ACC || j < 4) {   // predicated selects (opaque to the compiler, which would otherwise index v[] in local memory)
+        sel16(ac, v0, v1, j >> 1);
+      } else {
+        tmem_ld16_nowait(c.lane_base + (uint32_t)(C::PARK_COL + 32 * (j - 4) + h2 * CW), ac);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+      CPROF_LAP(2)
+      if constexpr (IOS & 1) {
+        // A parity wait is only meaningful once the PREVIOUS phase of the barrier has completed.  With an odd number of
+        // I/O stages a stage alternates between the half-teams, and a half-team three chunks ahead of the other would take
+        // the still-incomplete previous fill of the stage for its own (whole chunks of stale data): wait until the other
+        // half-team has seen that fill (chunk gc - IOS) land.
+        if (c.gc >= (uint32_t)IOS) {
+          const volatile uint32_t* seen = c.started + (grp ^ 1);
+          uint32_t spins = 0;
+          while (*seen + (uint32_t)IOS <= c.gc) {
+            if (++spins > tc::kSpinLimit) asm volatile("trap;");
+          }
+          __threadfence_block();
+        }
+      }
+      twait(&c.in_full[c.t], c.tph, 4, 1, i, j);
+      if constexpr (IOS & 1) {
+        if (c.q == 0 && c.h2 == 0 && c.lane == 0) *(volatile uint32_t*)(c.started + grp) = c.gc + 1u;   // chunks [0, gc] of mine have landed
+      }
+      CPROF_LAP(3)
+      float* b0 = (float*)(c.ioring + c.t * C::IO_STAGE);
+      float* b2 = b0 + CHUNK_BYTES / 4;
+      uint32_t hi[CW];
+      if (!(a.ablate & 4)) {
+        ta_math16<SWEEP, KIND, ACT>(a, i, 32 * j, c.rt, h2, b0, b2, ac, yb, yacc, hi);
+      } else {
+#pragma unroll
+        for (int k = 0; k < CW; ++k) hi[k] = 0u;
+      }
+      CPROF_LAP(4)
+      if constexpr (FEEDS) {
+        twait(&c.a_free[c.s], c.sph ^ 1, 4, 2, i, j);
+        CPROF_LAP(5)
+        tc::tc_fence_after();
+        const uint32_t taddr = c.lane_base + (uint32_t)(C::TA_COL0 + c.s * C::TA_COLS + h2 * CW);
+        tmem_st16(taddr, hi);
+        if constexpr (X3) {
+#pragma unroll
+          for (int k = 0; k < CW; ++k) hi[k] = __float_as_uint(lo_part(__uint_as_float(hi[k])));
+          tmem_st16(taddr + 32, hi);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc::tc_fence_before();
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> TMA store
+      CPROF_LAP(6)
+      if constexpr (COLSUM != 0) {
+        named_bar(1 + grp, 32 * EW / 2);                             // the half-team has written the whole chunk
+        if (h2 == 0) chunk_colsum(a, L, i, 32 * j, c.q, c.lane, b0, b2, first_tile);
+      }
+      __syncwarp();
+      if (c.lane == 0) {
+        if constexpr (FEEDS) tc::mbar_arrive(&c.a_ready[c.s]);
+        tc::mbar_arrive(&c.out_ready[c.t]);
+      }
+      CPROF_LAP(7)
+    }
+    if (FEEDS && ++c.s == TS) c.s = 0, c.sph ^= 1;
+    if (++c.t == IOS) c.t = 0, c.tph ^= 1;
+    ++c.gc;
+  }
+}
+// dispatch on the activation: the three codes fbsnn_api.cu's internal_act() produces for this precision
+template <int SWEEP, int KIND, bool X3>
+__device__ __forceinline__ void ta_link_act(const Args& a, const LinkD& L, int i, TeamCtx& c, float yb, float& yacc, bool first_tile) {
+  constexpr bool USES_ACT = (SWEEP == SWEEP_F && KIND != LINK_FIRST) || (SWEEP == SWEEP_A && KIND == LINK_MID) ||
+                            (SWEEP == SWEEP_T && KIND == LINK_LAST);
+  if constexpr (!USES_ACT) {
+    ta_link<SWEEP, KIND, X3, FBSNN_ACT_RELU>(a, L, i, c, yb, yacc, first_tile);
+  } else {
+    constexpr int SINE = X3 ? kActSineCW : kActSineFast, TANH = X3 ? FBSNN_ACT_TANH : kActTanhFast;
+    if (a.act == SINE) ta_link<SWEEP, KIND, X3, SINE>(a, L, i, c, yb, yacc, first_tile);
+    else if (a.act == FBSNN_ACT_RELU) ta_link<SWEEP, KIND, X3, FBSNN_ACT_RELU>(a, L, i, c, yb, yacc, first_tile);
+    else ta_link<SWEEP, KIND, X3, TANH>(a, L, i, c, yb, yacc, first_tile);
+  }
+}
+
+template <int SWEEP, bool X3>
+__global__ void __launch_bounds__(CfgT<X3>::NUM_THREADS, 1)
+chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
+  using C = CfgT<X3>;
+  constexpr int IOS = C::IO_STAGES, WS = C::W_STAGES, TS = C::TA_STAGES, EW = C::EPI_WARPS, CW = C::CW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wring = smem;
+  uint8_t* ioring = smem + WS * C::W_STAGE;
+  uint8_t* extra = ioring + IOS * C::IO_STAGE;
+  uint64_t* bars = (uint64_t*)extra;
+  uint64_t* w_full = bars;            // [4]  weight k-block landed
+  uint64_t* w_empty = bars + 4;       // [4]  MMAs that read it completed
+  uint64_t* in_full = bars + 8;       // [4]  input chunks landed (or: stage handed to the team)
+  uint64_t* out_ready = bars + 12;    // [4]  the team has written the stage's outputs (one arrival per warp)
+  uint64_t* io_free = bars + 16;      // [4]  the TMA stores have read the stage
+  uint64_t* a_ready = bars + 20;      // [8]  operand stage written to TMEM (one arrival per warp)
+  uint64_t* a_free = bars + 28;       // [8]  MMAs that read the operand stage completed
+  uint64_t* acc_full = bars + 36;     // [1]
+  uint64_t* acc_empty = bars + 37;    // [1]  every team warp holds its accumulator slice in registers
+  uint32_t* tmem_slot = (uint32_t*)(bars + 38);
+  float* ypart = (float*)(extra + 512);   // [3][128] head partial sums (F sweep)
+  uint32_t* started = (uint32_t*)(extra + 384);   // [2] progress of the two half-teams (odd IO_STAGES only)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < a.nlinks; ++i) {
+      const LinkD& L = a.link[i];
+      if (L.in0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.in0[i]) : "memory");
+      if (L.in2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.in2[i]) : "memory");
+      if (L.out0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.out0[i]) : "memory");
+      if (L.out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.out2[i]) : "memory");
+      if (L.feeds) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.whi[i]) : "memory");
+        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.wlo[i]) : "memory");
+      }
+    }
+    started[0] = started[1] = 0u;
+    for (int i = 0; i < WS; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < IOS; ++i) tc::mbar_init(&in_full[i], 1), tc::mbar_init(&out_ready[i], EW / 2), tc::mbar_init(&io_free[i], 1);
+    for (int i = 0; i < TS; ++i) tc::mbar_init(&a_ready[i], EW / 2), tc::mbar_init(&a_free[i], 1);
+    tc::mbar_init(&acc_full[0], 1), tc::mbar_init(&acc_empty[0], EW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  tc::pdl_trigger();
+  tc::pdl_wait();
+
+  // register re-allocation: the four control warps (one warpgroup) keep 24 registers each, the team's warps get 112 --
+  // their accumulator slice (32 registers) sits next to the working set of the fused epilogue
+  // (issued inside every role branch: after a merge point ptxas allocates for the smallest limit)
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (lane == 0) {
+      uint32_t ws = 0, wph = 0;
+      CPROF_BEGIN(true)
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          if (!L.feeds) continue;
+          const int nch = L.width >> 5, N = L.n_next;
+          const uint32_t bytes = (uint32_t)N * 128u * (X3 ? 2u : 1u);
+          for (int j = 0; j < nch; ++j) {
+            twait(&w_empty[ws], wph ^ 1, 0, 0, i, j);
+            CPROF_LAP(16)
+            uint8_t* dst = wring + ws * C::W_STAGE;
+            if (a.ablate & 16) {
+              tc::mbar_arrive(&w_full[ws]);
+            } else {
+              tc::mbar_expect_tx(&w_full[ws], bytes);
+              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
+                for (int c = 0; c < N / 32; ++c) {
+                  tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
+                  if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
+                }
+              } else {        // W[n][k] (k contiguous): one N x 32 box
+                tc::tma_load_2d(dst, &tm.whi[i], &w_full[ws], 32 * j, 0);
+                if (X3) tc::tma_load_2d(dst + 32768, &tm.wlo[i], &w_full[ws], 32 * j, 0);
+              }
+            }
+            CPROF_LAP(17)
+            if (++ws == WS) ws = 0, wph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== input producer: runs IOS chunks ahead of the team =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (lane == 0) {
+      uint32_t t = 0, ph = 0;
+      ChunkIt pf{(int)blockIdx.x, 0, 0};
+      auto prefetch_one = [&]() {   // row arrays of the chunks a few positions ahead -> L2
+        if (!pf.valid(a) || (a.ablate & 2)) return;
+        const LinkD& P = a.link[pf.link];
+        if (P.in0) tma_prefetch_2d(&tm.in0[pf.link], 32 * pf.j, pf.tile * 128);
+        if (P.in2) tma_prefetch_2d(&tm.in2[pf.link], 32 * pf.j, pf.tile * 128);
+        pf.next(a, (int)gridDim.x);
+      };
+      for (int p = 0; p < IOS + 4; ++p) prefetch_one();
+      CPROF_BEGIN(true)
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int m0 = tile * 128;
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          const int nch = L.width >> 5;
+          for (int j = 0; j < nch; ++j) {
+            twait(&io_free[t], ph ^ 1, 2, 0, i, j);
+            CPROF_LAP(14)
+            prefetch_one();
+            uint8_t* st = ioring + t * C::IO_STAGE;
+            if ((L.in0 || L.in2) && !(a.ablate & 2)) {
+              tc::mbar_expect_tx(&in_full[t], (uint32_t)CHUNK_BYTES * (uint32_t)((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0)));
+              if (L.in0) tc::tma_load_2d(st, &tm.in0[i], &in_full[t], 32 * j, m0);
+              if (L.in2) tc::tma_load_2d(st + CHUNK_BYTES, &tm.in2[i], &in_full[t], 32 * j, m0);
+            } else {
+              tc::mbar_arrive(&in_full[t]);
+            }
+            CPROF_LAP(15)
+            if (++t == IOS) t = 0, ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (lane == 0) {
+      uint32_t s = 0, sph = 0, ws = 0, wph = 0, mm = 0;
+      const uint32_t tmem_d = tmem_base;
+      CPROF_BEGIN(true)
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          if (!L.feeds) continue;
+          const int nch = L.width >> 5;
+          twait(&acc_empty[0], (mm & 1) ^ 1, 1, 0, i, 0);   // the accumulator of the MMA before this one is in registers
+          CPROF_LAP(8)
+          tc::tc_fence_after();
+          const uint32_t idesc = tc::make_idesc(L.n_next, false, L.b_mn != 0);
+          for (int j = 0; j < nch; ++j) {
+            twait(&a_ready[s], sph, 1, 1, i, j);
+            CPROF_LAP(9)
+            twait(&w_full[ws], wph, 1, 2, i, j);
+            CPROF_LAP(10)
+            tc::tc_fence_after();
+            if (!(a.ablate & 8)) {
+              const uint32_t ta = tmem_base + C::TA_COL0 + s * C::TA_COLS;
+              const uint32_t b0 = smem_u32(wring + ws * C::W_STAGE);
+              const uint32_t blo = b0 + 32768;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t db = L.b_mn ? tc::make_desc(b0 + k * 1024, 4096, 512, 1) : tc::make_desc(b0 + k * 32, 16, 1024, 2);
+                if (X3) {
+                  const uint64_t dbl = L.b_mn ? tc::make_desc(blo + k * 1024, 4096, 512, 1) : tc::make_desc(blo + k * 32, 16, 1024, 2);
+                  umma_tf32_ts(tmem_d, ta + 32 + 8 * k, db, idesc, (j | k) ? 1u : 0u);
+                  umma_tf32_ts(tmem_d, ta + 8 * k, dbl, idesc, 1u);
+                  umma_tf32_ts(tmem_d, ta + 8 * k, db, idesc, 1u);
+                } else {
+                  umma_tf32_ts(tmem_d, ta + 8 * k, db, idesc, (j | k) ? 1u : 0u);
+                }
+              }
+            }
+            tc::umma_commit(&w_empty[ws]);
+            tc::umma_commit(&a_free[s]);
+            CPROF_LAP(11)
+            if (++ws == WS) ws = 0, wph ^= 1;
+            if (++s == TS) s = 0, sph ^= 1;
+          }
+          tc::umma_commit(&acc_full[0]);
+          ++mm;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== store warp =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (lane == 0) {
+      uint32_t t = 0, ph = 0;
+      CPROF_BEGIN(true)
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int m0 = tile * 128;
+        for (int i = 0; i < a.nlinks; ++i) {
+          const LinkD& L = a.link[i];
+          const int nch = L.width >> 5;
+          for (int j = 0; j < nch; ++j) {
+            twait(&out_ready[t], ph, 3, 0, i, j);
+            CPROF_LAP(12)
+            const uint8_t* st = ioring + t * C::IO_STAGE;
+            const bool do_store = (L.out0 || L.out2) && !(a.ablate & 1);
+            if (do_store && L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
+            if (do_store && L.out2) tma_store_2d(&tm.out2[i], st + CHUNK_BYTES, 32 * j, m0);
+            if (do_store) {
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            tc::mbar_arrive(&io_free[t]);
+            CPROF_LAP(13)
+            if (++t == IOS) t = 0, ph ^= 1;
+          }
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
+    }
+  } else {
+    // ===================== epilogue: TWO half-teams of 8 warps (4 row quarters x 2 column halves) ==================
+    // Half-team g works on the chunks j = g, g + 2, ... of every link, so two chunks are in flight: one chunk's chain of
+    // waits, TMEM / shared-memory round trips and fences overlaps the other's.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int e = warp - C::EPI_WARP0;
+    TeamCtx c;
+    c.in_full = in_full, c.out_ready = out_ready, c.a_ready = a_ready, c.a_free = a_free, c.acc_full = acc_full, c.acc_empty = acc_empty;
+    c.ioring = ioring, c.ypart = ypart;
+    c.q = warp & 3;                  // TMEM lane quarter (rows 32q .. 32q+31 of the tile)
+    c.h2 = (e >> 2) & 1;             // column half: columns [16 h2, 16 h2 + 16) of the chunk
+    c.grp = e >> 3;                  // half-team
+    c.rt = c.q * 32 + lane, c.lane = lane;
+    c.lane_base = tmem_base + ((uint32_t)(c.q * 32) << 16);
+    c.t = c.tph = c.s = c.sph = c.dr = c.gc = 0;
+    c.started = started;
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, first_tile = false) {
+      const int row = tile * 128 + c.rt;
+      const bool valid = row < a.rows;
+      float yb = 0.f, yacc = 0.f;
+      if (SWEEP == SWEEP_T) yb = valid ? __ldg(a.ybar + row) : 0.f;
+      for (int i = 0; i < a.nlinks; ++i) {
+        const LinkD& L = a.link[i];
+        if (L.kind == LINK_FIRST) ta_link_act<SWEEP, LINK_FIRST, X3>(a, L, i, c, yb, yacc, first_tile);
+        else if (L.kind == LINK_MID) ta_link_act<SWEEP, LINK_MID, X3>(a, L, i, c, yb, yacc, first_tile);
+        else ta_link_act<SWEEP, LINK_LAST, X3>(a, L, i, c, yb, yacc, first_tile);
+        if (SWEEP == SWEEP_F && L.kind == LINK_LAST) {   // output head: u = h_L . wout + bout
+          const int hh = c.grp * 2 + c.h2;
+          if (hh > 0) ypart[(hh - 1) * 128 + c.rt] = yacc;
+          named_bar(3, 32 * EW);
+          if (hh == 0 && valid) {
+            float y = yacc;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) y += ypart[(k - 1) * 128 + c.rt];
+            a.Y[row] = y + __ldg(a.bout);
+          }
+          named_bar(3, 32 * EW);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // out[c] = sum over CTAs and row quarters of the chain kernels' column-sum partials (fixed order, double accumulation)
 struct ColFinJob {
   int slot, which, width;
@@ -903,16 +1509,11 @@ __global__ void chain_colsum_finish_kernel(const float* __restrict__ colacc, con
   j.out[c] = (float)acc;
 }
 
-// grid of a launch with clusters of `cl` CTAs: a multiple of cl, at most the SM count, every CTA with >= 1 tile slot
-inline int chain_grid(int ntiles, int num_sms, int cl) {
-  const int cap = num_sms / cl * cl;
-  const int want = (ntiles + cl - 1) / cl * cl;
-  return want < cap ? want : cap;
-}
-template <int SWEEP, bool X3, int CL>
-inline cudaError_t launch_chain_cl(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {
+inline int chain_grid(int ntiles, int num_sms) { return ntiles < num_sms ? ntiles : num_sms; }
+template <int SWEEP, bool X3>
+inline cudaError_t launch_chain(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {
   using C = Cfg<X3>;
-  auto kern = chain_kernel<SWEEP, X3, CL>;
+  auto kern = chain_kernel<SWEEP, X3>;
   static unsigned long long attr_devs = 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
@@ -921,13 +1522,21 @@ inline cudaError_t launch_chain_cl(const Maps& m, const Args& a, int num_sms, cu
     if (e != cudaSuccess) return e;
     attr_devs |= 1ull << dev;
   }
-  return tc::launch_pdl(kern, chain_grid(a.ntiles, num_sms, CL), C::NUM_THREADS, C::SMEM_BYTES, st, CL, m, a);
+  return tc::launch_pdl(kern, chain_grid(a.ntiles, num_sms), C::NUM_THREADS, C::SMEM_BYTES, st, 1, m, a);
 }
 template <int SWEEP, bool X3>
-inline cudaError_t launch_chain(const Maps& m, const Args& a, int num_sms, cudaStream_t st, int cl = 1) {
-  if (cl == 4) return launch_chain_cl<SWEEP, X3, 4>(m, a, num_sms, st);
-  if (cl == 2) return launch_chain_cl<SWEEP, X3, 2>(m, a, num_sms, st);
-  return launch_chain_cl<SWEEP, X3, 1>(m, a, num_sms, st);
+inline cudaError_t launch_chaint(const Maps& m, const Args& a, int num_sms, cudaStream_t st) {
+  using C = CfgT<X3>;
+  auto kern = chaint_kernel<SWEEP, X3>;
+  static unsigned long long attr_devs = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
+  if (!((attr_devs >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_devs |= 1ull << dev;
+  }
+  return tc::launch_pdl(kern, chain_grid(a.ntiles, num_sms), C::NUM_THREADS, C::SMEM_BYTES, st, 1, m, a);
 }
 // CTA-pair launch: a.ntiles = number of 256-row tiles; grid = 2 x min(tiles, SMs / 2), cluster (2,1,1)
 template <int SWEEP>

@@ -16,20 +16,20 @@ from tests import golden_util as gu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["cluster2", "cluster4", "cluster1", "pair"])
+@pytest.fixture(params=["tmem", "smem", "pair"])
 def chain_forced(request):
-    """Chained dispatch forced on.  "clusterN" = the chain kernel with N CTAs per cluster sharing every weight k-block by
-    TMA multicast (N = 1: no sharing); "pair" = the cta_group::2 kernel where the shape allows it (3xTF32, widths multiples
-    of 64)."""
+    """Chained dispatch forced on.  "tmem" = chaint_kernel (the default: operand of the next MMA in tensor memory), "smem" =
+    chain_kernel (operand in shared memory), "pair" = the cta_group::2 kernel where the shape allows it (3xTF32, widths
+    multiples of 64)."""
     import dnnpde_b200 as pde
     lib = pde._lib.load()
     old = lib.fbsnn_set_option(b"chain", 2)
+    old_ta = lib.fbsnn_set_option(b"chain_ta", 1 if request.param == "tmem" else 0)
     old_pair = lib.fbsnn_set_option(b"chain_pair", 1 if request.param == "pair" else 0)
-    old_cl = lib.fbsnn_set_option(b"chain_cluster", int(request.param[-1]) if request.param.startswith("cluster") else 1)
     yield lib
     lib.fbsnn_set_option(b"chain", old)
+    lib.fbsnn_set_option(b"chain_ta", old_ta)
     lib.fbsnn_set_option(b"chain_pair", old_pair)
-    lib.fbsnn_set_option(b"chain_cluster", old_cl)
 
 
 def _grads(sol):

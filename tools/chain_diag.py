@@ -39,12 +39,12 @@ def main():
     ap.add_argument("--problem", default="bsb")
     ap.add_argument("--fwd-only", action="store_true")
     ap.add_argument("--pair", type=int, default=0, help="chain_pair option (cta_group::2 chain kernel when eligible)")
-    ap.add_argument("--cluster", type=int, default=2, help="chain_cluster option (CTAs sharing a weight k-block)")
+    ap.add_argument("--ta", type=int, default=1, help="chain_ta option (operand of the next MMA in tensor memory)")
     args = ap.parse_args()
     import dnnpde_b200 as pde
     lib = pde._lib.load()
+    lib.fbsnn_set_option(b"chain_ta", args.ta)
     lib.fbsnn_set_option(b"chain_pair", args.pair)
-    lib.fbsnn_set_option(b"chain_cluster", args.cluster)
     D, M, N = args.dim, args.paths, args.steps
     layers = [int(x) for x in args.layers.split(",")] if args.layers else [D + 1] + 4 * [256] + [1]
     torch.manual_seed(1)
@@ -82,6 +82,14 @@ def main():
                 arrs[f"ws:{nm}[{l}]"] = ws_array(sol, lib, sp, M, with_grad, nm, l)
         res[mode] = arrs
         print(f"mode {mode}: loss {float(loss):.8e}", flush=True)
+    if hasattr(lib, "fbsnn_debug_chain_trap") or os.environ.get("FBSNN_LIB_PATH"):
+        try:
+            raw = ctypes.CDLL(os.environ["FBSNN_LIB_PATH"])
+            rec = (ctypes.c_uint * 8)()
+            raw.fbsnn_debug_chain_trap(rec, 1)
+            print("TRAP RECORD [set, block, role, what, link, chunk, parity, thread]:", list(rec), flush=True)
+        except Exception as e:   # noqa: BLE001
+            print("no trap record:", e)
     bad = 0
     for k in res[0]:
         a0, a2 = res[0][k], res[2][k]
@@ -104,6 +112,13 @@ def main():
             w = res[0][k].shape[-1] if res[0][k].dim() > 1 else 1
             note += f"  worst at flat {idx} (row {idx // w}, col {idx % w}): {float(a0[idx]):.6e} vs {float(a2[idx]):.6e}"
         print(f"{flag} {k:24s} rel_max_err {err:.3e} nan {nanc}{note}", flush=True)
+        if flag == "BAD" and k.startswith("ws:g[") and res[0][k].dim() == 2:
+            d2 = (res[0][k].double() - res[2][k].double()).abs() > 1e-4 * den
+            rows = torch.nonzero(d2.any(dim=1)).flatten()
+            print(f"     {int(rows.numel())} bad rows of {d2.shape[0]}; tiles {sorted(set((rows // 128).tolist()))[:12]}")
+            for r in rows[:6].tolist():
+                blocks = sorted(set((torch.nonzero(d2[r]).flatten() // 16).tolist()))
+                print(f"     row {r} (tile {r // 128}, row-in-tile {r % 128}): bad 16-col blocks {blocks}")
     print("DIAG", "FAIL" if bad else "PASS", args.precision, "fwd-only" if args.fwd_only else "full", f"M={M} layers={layers}")
     sys.exit(1 if bad else 0)
 

@@ -422,8 +422,9 @@ def measure_roofline(c, args, sol, batches, ms_per_step, m_loc, net, tf32_peak):
             "hbm": {"traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
                     "hbm_peak_gbs": pk["hbm"], "peak_source": pk["source"],
                     "traffic_gbs": (traffic / (ms_per_step * 1e-3) / 1e9) if traffic else None},
-            "kernel": ("chain_kernel / chain2_kernel (layer-chained tcgen05 sweeps, TMA-fed) + gemm_tc2g_kernel (weight "
-                       "gradients, cta_group::2, A operand in TMEM)") if any(r["sweep"].endswith("*") for r in table)
+            "kernel": ("chaint_kernel (layer-chained tcgen05 sweeps: operand of the next MMA written to TMEM by the fused "
+                       "epilogue, TMA-fed row-array I/O ring) + gemm_tc2g_kernel (weight gradients, cta_group::2, A operand "
+                       "in TMEM)") if any(r["sweep"].endswith("*") for r in table)
             else "gemm_tc*_kernel (tcgen05, one launch per dense layer)" if any(r["tensor_cores"] for r in table)
             else "gemm_simt_kernel (fp32 FMA)",
             "dominant_launch": dom, "launch_table": table, "dense_ms_per_step": dense_ms,

@@ -78,7 +78,10 @@ const char* fbsnn_last_error(void);
 int fbsnn_version(void);
 /* Run-time switch of the kernel dispatch (tests, A/B measurements; no reference counterpart).  "chain": 0 = one launch
  * per dense layer, 1 = layer-chained sweep kernels once the row tiles fill the chip (default), 2 = always when the
- * network is eligible (FC, widths multiples of 32 in [64, 256], tensor-core precision).  Returns the previous value. */
+ * network is eligible (FC, widths multiples of 32 in [64, 256], tensor-core precision).  "chain_ta": which chained kernel:
+ * 0 = operand of the next layer's MMA in shared memory (chain_kernel), 1 = in tensor memory where that measured faster
+ * (default), 2 = in tensor memory for every eligible sweep (widths multiples of 64).  "chain_pair": 0 | 1 = cta_group::2
+ * form of chain_kernel.  Returns the previous value. */
 int fbsnn_set_option(const char* name, int value);
 /* Measurement hooks used by bench.py: number of kernels this library has launched since it was loaded; and
  * optional CUDA-event timing of every dense-layer launch (enable, run, synchronise, read).

@@ -24,7 +24,7 @@ def chain_forced(request):
     import dnnpde_b200 as pde
     lib = pde._lib.load()
     old = lib.fbsnn_set_option(b"chain", 2)
-    old_ta = lib.fbsnn_set_option(b"chain_ta", 1 if request.param == "tmem" else 0)
+    old_ta = lib.fbsnn_set_option(b"chain_ta", 2 if request.param == "tmem" else 0)
     old_pair = lib.fbsnn_set_option(b"chain_pair", 1 if request.param == "pair" else 0)
     yield lib
     lib.fbsnn_set_option(b"chain", old)

@@ -641,6 +641,14 @@ static void chain_base(const FbsnnSpec* s, const Plan& p, const Net& n, chain::A
     ablate = e ? atoi(e) : 0;
   }
   a.ablate = ablate;
+  static int pf = -1, hints = -1;
+  if (pf < 0) {
+    const char* e = getenv("FBSNN_CHAIN_PF");
+    pf = e ? atoi(e) : 7;
+    const char* h = getenv("FBSNN_CHAIN_HINT");
+    hints = h ? atoi(h) : 7;   // measured (M = 65 536, 3xTF32, sum of the four sweeps): 43.4 ms with 7, 43.7 with 5, 45.1 with 0
+  }
+  a.pf_dist = pf, a.hints = hints;
 }
 
 // F and A sweeps as two launches; leaves g_l, a_l, delta_l (, s_l for l < L), Y and Du_full in the workspace

@@ -52,6 +52,9 @@ struct Maps {
 };
 struct Args {
   int nlinks, rows, ntiles, act, with_s;
+  int pf_dist;  // chaint_kernel: row-array chunks pulled into L2 ahead of their TMA load (FBSNN_CHAIN_PF)
+  int hints;    // chaint_kernel L2 policies (FBSNN_CHAIN_HINT): bit 0 = row-array stores evict_first, bit 1 = row-array loads
+                // evict_first, bit 2 = weight k-blocks evict_last (re-read by every tile while the row arrays stream through)
   int ablate;   // measurement only (FBSNN_CHAIN_ABLATE): 1 no TMA stores, 2 no input loads, 4 no epilogue math, 8 no MMAs, 16 no weight loads
   LinkD link[kMaxLinks];
   const float* bias[kMaxLinks];   // F: bias of the layer whose pre-activation link i receives
@@ -87,6 +90,27 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, const void* src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -1288,6 +1312,7 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (lane == 0) {
       uint32_t ws = 0, wph = 0;
+      const uint64_t wpol = l2_evict_last_policy();
       CPROF_BEGIN(true)
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         for (int i = 0; i < a.nlinks; ++i) {
@@ -1303,7 +1328,17 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
               tc::mbar_arrive(&w_full[ws]);
             } else {
               tc::mbar_expect_tx(&w_full[ws], bytes);
-              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
+              if (a.hints & 4) {   // weights: L2 evict_last (they are re-read by every tile; the row arrays stream through)
+                if (L.b_mn) {
+                  for (int c = 0; c < N / 32; ++c) {
+                    tma_load_2d_hint(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j, wpol);
+                    if (X3) tma_load_2d_hint(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j, wpol);
+                  }
+                } else {
+                  tma_load_2d_hint(dst, &tm.whi[i], &w_full[ws], 32 * j, 0, wpol);
+                  if (X3) tma_load_2d_hint(dst + 32768, &tm.wlo[i], &w_full[ws], 32 * j, 0, wpol);
+                }
+              } else if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
                 for (int c = 0; c < N / 32; ++c) {
                   tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
                   if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
@@ -1332,7 +1367,8 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
         if (P.in2) tma_prefetch_2d(&tm.in2[pf.link], 32 * pf.j, pf.tile * 128);
         pf.next(a, (int)gridDim.x);
       };
-      for (int p = 0; p < IOS + 4; ++p) prefetch_one();
+      const uint64_t pol = l2_evict_first_policy();
+      for (int p = 0; p < a.pf_dist; ++p) prefetch_one();
       CPROF_BEGIN(true)
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int m0 = tile * 128;
@@ -1346,8 +1382,13 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
             uint8_t* st = ioring + t * C::IO_STAGE;
             if ((L.in0 || L.in2) && !(a.ablate & 2)) {
               tc::mbar_expect_tx(&in_full[t], (uint32_t)CHUNK_BYTES * (uint32_t)((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0)));
-              if (L.in0) tc::tma_load_2d(st, &tm.in0[i], &in_full[t], 32 * j, m0);
-              if (L.in2) tc::tma_load_2d(st + CHUNK_BYTES, &tm.in2[i], &in_full[t], 32 * j, m0);
+              if (a.hints & 2) {
+                if (L.in0) tma_load_2d_hint(st, &tm.in0[i], &in_full[t], 32 * j, m0, pol);
+                if (L.in2) tma_load_2d_hint(st + CHUNK_BYTES, &tm.in2[i], &in_full[t], 32 * j, m0, pol);
+              } else {
+                if (L.in0) tc::tma_load_2d(st, &tm.in0[i], &in_full[t], 32 * j, m0);
+                if (L.in2) tc::tma_load_2d(st + CHUNK_BYTES, &tm.in2[i], &in_full[t], 32 * j, m0);
+              }
             } else {
               tc::mbar_arrive(&in_full[t]);
             }
@@ -1412,6 +1453,7 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (lane == 0) {
       uint32_t t = 0, ph = 0;
+      const uint64_t pol = l2_evict_first_policy();
       CPROF_BEGIN(true)
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int m0 = tile * 128;
@@ -1423,8 +1465,13 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
             CPROF_LAP(12)
             const uint8_t* st = ioring + t * C::IO_STAGE;
             const bool do_store = (L.out0 || L.out2) && !(a.ablate & 1);
-            if (do_store && L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
-            if (do_store && L.out2) tma_store_2d(&tm.out2[i], st + CHUNK_BYTES, 32 * j, m0);
+            if (do_store && (a.hints & 1)) {
+              if (L.out0) tma_store_2d_hint(&tm.out0[i], st, 32 * j, m0, pol);
+              if (L.out2) tma_store_2d_hint(&tm.out2[i], st + CHUNK_BYTES, 32 * j, m0, pol);
+            } else if (do_store) {
+              if (L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
+              if (L.out2) tma_store_2d(&tm.out2[i], st + CHUNK_BYTES, 32 * j, m0);
+            }
             if (do_store) {
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

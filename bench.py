@@ -70,11 +70,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Starts sampling (call before the warm-up: nvidia-smi takes a few hundred ms to deliver its first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -82,28 +84,44 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return None
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])), mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lines):
+            sm, mx, reasons = [], [], set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])), mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        window = "timed region"
+        inside = [x for x in self.lines if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or 1e30) + 0.05]
+        sm, mx, reasons = parse(inside)
+        if not sm:   # a timed region shorter than one sampling period: the samples under load since the warm-up
+            window = "warm-up + timed region (the timed region was shorter than one sampling period)"
+            sm, mx, reasons = parse(self.lines[-8:])
         if not sm:
             return None
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -308,18 +326,22 @@ def time_steps(c, sol, batches, steps, warmup, sample_clocks=False):
         b = batches[i % len(batches)] if batches else (None, None)
         sol._step(*b, loss_buf[k:k + 1], False, i, alias_inputs=bool(batches))
 
-    for i in range(warmup):                                  # warm-up (captures one CUDA graph per resident batch)
-        step(i, i)
-    c.barrier()
     clocks = ClockSampler(c.local) if sample_clocks else None
     if clocks:
         clocks.start()
+    for i in range(warmup):                                  # warm-up (captures one CUDA graph per resident batch)
+        step(i, i)
+    c.barrier()
+    if clocks:
+        clocks.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         step(i, warmup + i)
     e1.record()
     c.barrier()
+    if clocks:
+        clocks.mark_end()
     ms = c.max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if clocks else None
     return ms / steps, int(launches), clk, float(loss_buf[warmup + steps - 1])

@@ -516,12 +516,15 @@ static int chain_mode() {
   }
   return g_opt_chain;
 }
+static bool chain_use_ta(const Plan& p);
 static bool chain_eligible(const FbsnnSpec* s, const Plan& p) {
   if (chain_mode() == 0 || p.nais || !p.tf32) return false;
   if (p.ldx % 32 || p.ldx > 256 || p.L + 1 > chain::kMaxLinks) return false;
   for (int l = 1; l <= p.L; ++l)
     if (p.H[l] % 32 || p.H[l] < 64 || p.H[l] > 256) return false;
-  if (chain_mode() == 1 && p.rows < (long long)num_sms() * 128) return false;
+  // below one row tile per SM the shared-memory chain kernel loses to the narrow-tile per-layer launches (more CTAs at work);
+  // chaint_kernel still wins there: 4 launches instead of 16 (M = 100, 40 tiles: 0.29 vs 0.40 ms of dense launches per step)
+  if (chain_mode() == 1 && p.rows < (long long)num_sms() * 128 && !chain_use_ta(p)) return false;
   return true;
 }
 // CTA-pair form of the chained sweeps (chain2_kernel): 3xTF32, every MMA width a multiple of 64 (each CTA stages half of

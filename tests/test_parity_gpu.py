@@ -133,7 +133,8 @@ def test_tf32_variant_runs_on_tensor_cores():
     out = (ctypes.c_double * 8)()
     assert lib.fbsnn_dense_timing_read(out) == 0
     lib.fbsnn_dense_timing(0)
-    assert out[0] == 19 and out[3] == 19, list(out)
+    # 4 chained sweeps + 4 weight-gradient contractions (19 launches with the per-layer dispatch, option chain = 0)
+    assert out[0] in (8, 19) and out[3] == out[0], list(out)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -743,6 +743,8 @@ struct OptState {
   float clip_coef, step_size, bc2_sqrt, grad_norm;
   long long rng_iter;                                // Philox iteration counter of fbsnn_train_step (never reset)
   int skip;                                          // 1: this iteration's gradient was not finite, no update
+  long long epoch;                                   // optimiser steps taken so far, NEVER rewound: epoch of the peer all-reduce's
+                                                     // cross-GPU barrier (rng_iter is rewound after a graph-capture dry run)
 };
 
 __global__ void gradsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
@@ -761,7 +763,7 @@ __global__ void gradsq_kernel(const float* __restrict__ g, long long n, float* _
 //
 // Every rank's gradient kernels write into a symmetric buffer that all peers have mapped:
 //   floats [0, n_grad) gradient | [n_grad] loss | ... | u32 flags at float offset flag_off: ready[16], done[16]
-// Protocol for epoch e = (Philox iteration counter + 1), identical on all ranks and never reset:
+// Protocol for epoch e = (OptState::epoch + 1), identical on all ranks and never rewound:
 //   1. block 0 stores e into ready[rank] of every peer (release.sys: this rank's gradient kernels finished
 //      earlier on the stream); every block spins (acquire.sys) until its own ready[0..W) >= e
 //   2. all blocks sum the W buffers in rank order 0..W-1 (so every rank gets bit-identical sums) with L1-bypassing
@@ -810,7 +812,7 @@ struct PeerArgs {
 };
 __global__ void peer_reduce_kernel(PeerArgs a, float* __restrict__ out, float* __restrict__ part) {
   __shared__ float red[32];
-  const unsigned epoch = (unsigned)(a.st->rng_iter + 1);
+  const unsigned epoch = (unsigned)(a.st->epoch + 1);
   if (blockIdx.x == 0 && threadIdx.x < a.world) {
     __threadfence_system();
     st_release_sys(reinterpret_cast<unsigned*>(a.peers[threadIdx.x] + a.flag_off) + a.rank, epoch);
@@ -843,7 +845,7 @@ __global__ void peer_reduce_kernel(PeerArgs a, float* __restrict__ out, float* _
 }
 // start of an iteration: every peer has finished reading this rank's buffer in the previous epoch
 __global__ void peer_wait_kernel(const float* local_buf, long long flag_off, int world, const OptState* st) {
-  const unsigned epoch = (unsigned)st->rng_iter;
+  const unsigned epoch = (unsigned)st->epoch;
   if (epoch != 0 && threadIdx.x < world)
     peer_spin(reinterpret_cast<const unsigned*>(local_buf + flag_off) + kPeerMaxWorld + threadIdx.x, epoch);
 }
@@ -889,6 +891,7 @@ __global__ void opt_prepare_kernel(const float* __restrict__ part, int npart, Fb
     float coef = 1.f;
     if (hp.max_grad_norm > 0.0) coef = fminf((float)hp.max_grad_norm / (norm + 1e-6f), 1.f);
     st->rng_iter += 1;
+    st->epoch += 1;
     st->grad_norm = norm;
     st->skip = (hp.skip_nonfinite != 0.0 && !isfinite(norm)) ? 1 : 0;
     if (st->skip) return;

@@ -615,9 +615,9 @@ class FBSNN(ABC):
             elif host_batch:
                 gs["t"], gs["W"] = torch.empty_like(t_b), torch.empty_like(W_b)
                 gs["t"].copy_(t_b), gs["W"].copy_(W_b)
-            # capture needs a warm-up run on a side stream; keep it side-effect free by restoring the state.  The Philox
-            # iteration counter (bytes 24..32 of the optimiser state) is restored on one GPU only: on several GPUs it is
-            # also the epoch of the peer barrier, which must never run backwards (every rank advances it alike)
+            # capture needs a warm-up run on a side stream; keep it side-effect free by restoring the state (Adam step,
+            # Philox iteration counter).  The one thing that is NOT rewound is the epoch of the peer all-reduce's cross-GPU
+            # barrier (bytes 40..48 of the optimiser state): every rank advances it alike and it must never run backwards
             fp = self._fp
             saved = [x.clone() for x in (fp.flat, fp.exp_avg, fp.exp_avg_sq, self._opt_state)]
             tsaved = track["state"].clone() if track is not None else None
@@ -637,9 +637,9 @@ class FBSNN(ABC):
             for dst, src in zip((fp.flat, fp.exp_avg, fp.exp_avg_sq), saved):
                 dst.copy_(src)
             if dp:
-                rng_now = self._opt_state[24:32].clone()
+                epoch_now = self._opt_state[40:48].clone()
                 self._opt_state.copy_(saved[3])
-                self._opt_state[24:32].copy_(rng_now)
+                self._opt_state[40:48].copy_(epoch_now)
             else:
                 self._opt_state.copy_(saved[3])
             if track is not None:

@@ -158,8 +158,9 @@ int fbsnn_track_min(const float* loss, float* state, const void* opt_state, cons
  * FBSNN_OPT_STATE_BYTES of device memory: int64 step counter at byte 0 (zero-initialised by the caller when the
  * optimizer is created -- the reference builds a fresh Adam per train() call, DeepBSDE.py:272), then float
  * clip_coef @8, step_size @12, sqrt(bias_correction2) @16, grad_norm @20, int32 skip flag @32, int64 Philox iteration counter @24 (keep it
- * across optimisers: fbsnn_train_step adds it to `iteration`), and reduction scratch from byte 64.
- * Both counters are advanced on the device, so the call can be replayed from a CUDA graph. */
+ * across optimisers: fbsnn_train_step adds it to `iteration`), int64 count of optimiser steps ever taken @40 (the epoch of
+ * the peer all-reduce's barrier: never reset or rewound), and reduction scratch from byte 64.
+ * All counters are advanced on the device, so the call can be replayed from a CUDA graph. */
 #define FBSNN_OPT_STATE_BYTES 2048
 int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads, float* exp_avg,
                     float* exp_avg_sq, int64_t n_params, void* opt_state, void* stream);
@@ -174,7 +175,7 @@ int fbsnn_adam_step(const FbsnnAdam* host_hp, float* params, const float* grads,
  * fbsnn_loss_grad  ->  fbsnn_peer_allreduce_adam.  One kernel signals/waits the peers (release/acquire at system
  * scope, bounded spin), sums the W buffers in rank order (=> bit-identical parameters on every rank) into
  * grad_sum (local, n_params + 4 floats; [n_params] = global loss) and accumulates the squared norm; clip + Adam
- * follow on the same stream.  The epoch is the Philox iteration counter of opt_state (never reset), so all ranks
+ * follow on the same stream.  The epoch is the step count @40 of opt_state (never reset or rewound), so all ranks
  * must have taken the same number of optimiser steps; the sequence is CUDA-graph capturable. */
 int fbsnn_peer_buffer_floats(int64_t n_params, int64_t* flag_offset_out, int64_t* total_out);
 int fbsnn_peer_wait(const float* local_buf, int64_t n_params, int world, const void* opt_state, void* stream);

@@ -538,9 +538,10 @@ static int chain_pair_mode() {
   return g_opt_chain_pair;
 }
 // Operand of the next MMA in tensor memory (chaint_kernel).  Option "chain_ta" / FBSNN_CHAIN_TA: 0 = the shared-memory forms
-// above, 1 (default) = where measured faster (3xTF32: every sweep, 46.0 vs 50.1 ms for the four sweeps at M = 65 536;
-// single-pass TF32: the F sweep only, 6.7 vs 7.5 ms -- its A / T sweeps are bound by the row-array traffic, where the
-// shared-memory kernel's deeper operand ring does better, 10.4 / 11.5 vs 12.1 / 13.5 ms), 2 = every eligible sweep.
+// above, 1 (default) = where measured faster (3xTF32: every sweep, 43.4 vs 50.1 ms for the four sweeps at M = 65 536;
+// single-pass TF32: the F and B sweeps, 7.0 / 6.4 vs 7.8-8.3 / 6.7-7.1 ms -- its A / T sweeps are bound by the row-array
+// traffic, where the shared-memory kernel's deeper operand ring does better, 10.0 / 10.5 vs 10.8 / 11.3 ms), 2 = every
+// eligible sweep.
 static int g_opt_chain_ta = -1;
 static int chain_ta_mode() {
   if (g_opt_chain_ta < 0) {
@@ -606,7 +607,7 @@ static int chain_launch(const FbsnnSpec* s, const Plan& p, const chain::Maps& m,
   chain_timing_begin(slot, a, what, st);
   ++g_launches;
   cudaError_t e;
-  if (chain_use_ta(p) && (p.x3 || SWEEP == chain::SWEEP_F || chain_ta_mode() == 2)) {
+  if (chain_use_ta(p) && (p.x3 || SWEEP == chain::SWEEP_F || SWEEP == chain::SWEEP_B || chain_ta_mode() == 2)) {
     e = s->precision == FBSNN_PREC_TF32X3 ? chain::launch_chaint<SWEEP, true>(m, a, num_sms(), st)
                                           : chain::launch_chaint<SWEEP, false>(m, a, num_sms(), st);
   } else if (chain_use_pair(p)) {

@@ -53,7 +53,7 @@ struct Maps {
 struct Args {
   int nlinks, rows, ntiles, act, with_s;
   int pf_dist;  // chaint_kernel: row-array chunks pulled into L2 ahead of their TMA load (FBSNN_CHAIN_PF)
-  int hints;    // chaint_kernel L2 policies (FBSNN_CHAIN_HINT): bit 0 = row-array stores evict_first, bit 1 = row-array loads
+  int hints;    // chaint_kernel / chain_kernel L2 policies (FBSNN_CHAIN_HINT): bit 0 = row-array stores evict_first, bit 1 = row-array loads
                 // evict_first, bit 2 = weight k-blocks evict_last (re-read by every tile while the row arrays stream through)
   int ablate;   // measurement only (FBSNN_CHAIN_ABLATE): 1 no TMA stores, 2 no input loads, 4 no epilogue math, 8 no MMAs, 16 no weight loads
   LinkD link[kMaxLinks];
@@ -350,6 +350,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     // ===================== weight producer =====================
     if (lane == 0) {
       uint32_t ws = 0, wph = 0;
+      const uint64_t wpol = l2_evict_last_policy();
       for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int i = 0; i < a.nlinks; ++i) {
           const LinkD& L = a.link[i];
@@ -363,7 +364,17 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
               tc::mbar_arrive(&w_full[ws]);
             } else {
               tc::mbar_expect_tx(&w_full[ws], bytes);
-              if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
+              if (a.hints & 4) {   // weights: L2 evict_last
+                if (L.b_mn) {
+                  for (int c = 0; c < N / 32; ++c) {
+                    tma_load_2d_hint(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j, wpol);
+                    if (X3) tma_load_2d_hint(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j, wpol);
+                  }
+                } else {
+                  tma_load_2d_hint(dst, &tm.whi[i], &w_full[ws], 32 * j, 0, wpol);
+                  if (X3) tma_load_2d_hint(dst + 32768, &tm.wlo[i], &w_full[ws], 32 * j, 0, wpol);
+                }
+              } else if (L.b_mn) {   // W[k][n] (n contiguous): 32 x 32 boxes, 128B swizzle with 32B atoms
                 for (int c = 0; c < N / 32; ++c) {
                   tc::tma_load_2d(dst + c * 4096, &tm.whi[i], &w_full[ws], 32 * c, 32 * j);
                   if (X3) tc::tma_load_2d(dst + 32768 + c * 4096, &tm.wlo[i], &w_full[ws], 32 * c, 32 * j);
@@ -382,6 +393,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     // ===================== input producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      const uint64_t pol = l2_evict_first_policy();
       // the row arrays of the chunks a few positions ahead are pulled into L2 now, so that the TMA load issued when the
       // stage frees up pays an L2 hit instead of the HBM latency (that latency sits inside the stage's occupancy)
       ChunkIt pf{(int)blockIdx.x, 0, 0};
@@ -405,8 +417,13 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
             uint64_t* bar = &in_full[s];
             if ((L.in0 || L.in2) && !(a.ablate & 2)) {
               tc::mbar_expect_tx(bar, (uint32_t)CHUNK_BYTES * (uint32_t)((L.in0 ? 1 : 0) + (L.in2 ? 1 : 0)));
-              if (L.in0) tc::tma_load_2d(st, &tm.in0[i], bar, 32 * j, m0);
-              if (L.in2) tc::tma_load_2d(st + C::B2_OFF, &tm.in2[i], bar, 32 * j, m0);
+              if (a.hints & 2) {   // row arrays stream through: L2 evict_first
+                if (L.in0) tma_load_2d_hint(st, &tm.in0[i], bar, 32 * j, m0, pol);
+                if (L.in2) tma_load_2d_hint(st + C::B2_OFF, &tm.in2[i], bar, 32 * j, m0, pol);
+              } else {
+                if (L.in0) tc::tma_load_2d(st, &tm.in0[i], bar, 32 * j, m0);
+                if (L.in2) tc::tma_load_2d(st + C::B2_OFF, &tm.in2[i], bar, 32 * j, m0);
+              }
             } else {
               tc::mbar_arrive(bar);
             }
@@ -473,6 +490,7 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
     // ===================== store warp =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      const uint64_t pol = l2_evict_first_policy();
       for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int m0 = tile * 128;
         for (int i = 0; i < a.nlinks; ++i) {
@@ -482,8 +500,13 @@ chain_kernel(const __grid_constant__ Maps tm, const Args a) {
             cwait(&a_ready[s], ph, 3, 0, i, j);
             const uint8_t* st = aring + s * C::A_STAGE;
             const bool do_store = (L.out0 || L.out2) && !(a.ablate & 1);
-            if (do_store && L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
-            if (do_store && L.out2) tma_store_2d(&tm.out2[i], st + C::B2_OFF, 32 * j, m0);
+            if (do_store && (a.hints & 1)) {
+              if (L.out0) tma_store_2d_hint(&tm.out0[i], st, 32 * j, m0, pol);
+              if (L.out2) tma_store_2d_hint(&tm.out2[i], st + C::B2_OFF, 32 * j, m0, pol);
+            } else if (do_store) {
+              if (L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
+              if (L.out2) tma_store_2d(&tm.out2[i], st + C::B2_OFF, 32 * j, m0);
+            }
             if (do_store) {
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -52,6 +52,8 @@ SHAPES = [
     (100, 40, 50, [101, 256, 256, 256, 256, 1], "Sine", "bsb"),      # the benchmarked network, ragged last tile
     (100, 3, 50, [101, 256, 256, 256, 256, 1], "Sine", "bsb"),       # two tiles
     (100, 700, 50, [101, 256, 256, 256, 256, 1], "Sine", "bsb"),     # 279 tiles: several tiles per CTA (pair: 140 pairs of 74)
+    (100, 2000, 50, [101, 256, 256, 256, 256, 1], "Sine", "bsb"),    # 797 tiles, 5-6 per CTA on a busy chip: the regime in which a
+                                                                     # half-team of chaint_kernel can run three chunks ahead of the other
     (126, 90, 30, [127, 128, 192, 64, 1], "Tanh", "bsb"),            # pair-eligible mixed widths, 22 tiles
     (10, 300, 7, [11, 64, 128, 64, 1], "Tanh", "bsb"),               # ldx = 32, mixed widths
     (20, 77, 12, [21, 96, 96, 1], "ReLU", "hjb"),                    # two layers, odd chunk counts, |Z|^2 driver

@@ -64,7 +64,8 @@ struct Plan {
   bool nais;
   long long rows;
   int loss_blocks, col_blocks, col_rows_per_block, wg_split, wg_chunk, gsq_blocks;
-  size_t wg_stride;   // floats between the per-layer split-K partial buffers (FC)
+  size_t wg_stride;   // floats between the per-contraction split-K partial buffers
+  int wg_slots;       // how many of them the workspace holds
   // offsets in floats
   size_t xin, sdw, Y, zf, V, ev, ybar, inc, zraw, part_loss, part_wg, part_col, part_gsq, umask;
   size_t g[kMaxL + 2], a[kMaxL + 2], delta[kMaxL + 2], szz[kMaxL + 2], hd[kMaxL + 2], h[kMaxL + 2],
@@ -185,7 +186,9 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
       wg = std::max(wg, (size_t)p.H[l] * (size_t)p.ldx);
     }
     p.wg_stride = (wg * p.wg_split + 63) / 64 * 64;
-    p.part_wg = take(p.wg_stride * (p.nais ? 1 : p.L));   // FC: one partial buffer per layer, reduced together
+    // one split-K partial buffer per weight-gradient contraction (FC: L, NAIS-Net: 2 L - 1), reduced together in one launch
+    p.wg_slots = p.nais ? (2 * p.L - 1 <= kMaxRedJobs ? 2 * p.L - 1 : 1) : p.L;
+    p.part_wg = take(p.wg_stride * p.wg_slots);
     p.part_col = take((size_t)kMaxColJobs * std::max(p.col_blocks, 256) * 1024);   // 256 >= CTAs of the tcgen05 grid
     p.part_gsq = take(p.gsq_blocks);
     if (p.tf32 && !p.nais) p.chain_col = take((size_t)num_sms() * chain::kMaxLinks * 2 * 1024);
@@ -496,7 +499,7 @@ static int nais_prepare(const FbsnnSpec* s, const Plan& p, const Net& n, float* 
     g.seg[0] = GemmSeg{n.Wraw[l], n.Wraw[l], H, H, H};
     int rc = dense<false, false>(s, g, EpiStore{ws + p.Rm[l], H}, 1, st, "nais RtR", false);
     if (rc) return rc;
-    nais_project_kernel<<<1, 1024, 0, st>>>(ws + p.Rm[l], H, s->nais_eps, ws + p.Bm[l], ws + p.nstate[l]);
+    nais_project_kernel<<<(H * H + 1023) / 1024, 1024, 0, st>>>(ws + p.Rm[l], H, s->nais_eps, ws + p.Bm[l], ws + p.nstate[l]);
     LAUNCH_CHECK("nais_project");
   }
   return 0;
@@ -956,33 +959,37 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
   // ---- G contractions ------------------------------------------------------------------------------------
   RedJobs red{};
   red.nsplit = p.wg_split;
-  RedJobs* defer = p.nais ? nullptr : &red;   // FC: the L contractions run back to back, one reduction launch after
+  // the contractions run back to back into their own partial buffers, one reduction launch after (NAIS-Net networks too
+  // deep for kMaxRedJobs buffers reduce every contraction on its own)
+  RedJobs* defer = (!p.nais || p.wg_slots > 1) ? &red : nullptr;
   const size_t wg_stride = p.wg_stride;
+  int slot = 0;
+  auto nais_wbar = [&](int l) -> int {   // gradient through the stability projection: Wbar_l = W_l (Rbar + Rbar^T)
+    const int H = p.H[l];
+    nais_project_bwd_kernel<<<(H * H + 1023) / 1024, 1024, 0, st>>>(ws + p.Bbar[l], ws + p.Rm[l], H, ws + p.nstate[l], ws + p.Sm[l]);
+    LAUNCH_CHECK("nais_project_bwd");
+    GemmArgs g{};
+    g.M = H, g.N = H, g.Nb = H, g.kchunk = 0, g.nseg = 1;
+    g.seg[0] = GemmSeg{n.Wraw[l], ws + p.Sm[l], H, H, H};
+    return dense<true, false>(s, g, EpiStore{grads + s->off_W[l], H}, 1, st, "nais Wbar", false);
+  };
   for (int l = 1; l <= p.L; ++l) {
     int rc;
-    const size_t poff = defer ? (size_t)(l - 1) * wg_stride : 0;
     if (l == 1) {
       rc = wgrad(s, p, ws, ws + p.szz[1], ws + p.xin, ws + p.delta[1], ws + p.V, p.H[1], p.ldx, p.d_in, p.ldx,
-                 grads + s->off_W[1], p.d_in, st, defer, poff);
+                 grads + s->off_W[1], p.d_in, st, defer, defer ? (size_t)(slot++) * wg_stride : 0);
       if (rc) return rc;
       continue;
     }
     float* dst = p.nais ? ws + p.Bbar[l] : grads + s->off_W[l];
     rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.h[l - 1], ws + p.delta[l], ws + p.hd[l - 1], p.H[l], p.H[l - 1],
-               p.H[l - 1], p.H[l - 1], dst, p.H[l - 1], st, defer, poff);
+               p.H[l - 1], p.H[l - 1], dst, p.H[l - 1], st, defer, defer ? (size_t)(slot++) * wg_stride : 0);
     if (rc) return rc;
     if (p.nais) {
       rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.xin, ws + p.delta[l], ws + p.V, p.H[l], p.ldx, p.d_in, p.ldx,
-                 grads + s->off_Win[l], p.d_in, st);
+                 grads + s->off_Win[l], p.d_in, st, defer, defer ? (size_t)(slot++) * wg_stride : 0);
       if (rc) return rc;
-      const int H = p.H[l];
-      nais_project_bwd_kernel<<<1, 1024, 0, st>>>(ws + p.Bbar[l], ws + p.Rm[l], H, ws + p.nstate[l], ws + p.Sm[l]);
-      LAUNCH_CHECK("nais_project_bwd");
-      GemmArgs g{};
-      g.M = H, g.N = H, g.Nb = H, g.kchunk = 0, g.nseg = 1;
-      g.seg[0] = GemmSeg{n.Wraw[l], ws + p.Sm[l], H, H, H};
-      rc = dense<true, false>(s, g, EpiStore{grads + s->off_W[l], H}, 1, st, "nais Wbar", false);
-      if (rc) return rc;
+      if (!defer && (rc = nais_wbar(l))) return rc;
     }
   }
   if (defer && red.njobs > 0) {
@@ -991,6 +998,11 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     reduce_partials_batched_kernel<<<dim3((maxn + 255) / 256, red.njobs), 256, 0, st>>>(red);
     LAUNCH_CHECK("reduce_partials_batched");
   }
+  if (p.nais && defer)
+    for (int l = 2; l <= p.L; ++l) {
+      int rc = nais_wbar(l);
+      if (rc) return rc;
+    }
   if (chained) return 0;   // bias and output-weight gradients came out of the chained sweeps' fused column sums
   // ---- bias / output-layer gradients: column sums -----------------------------------------------------------
   ColJobs js{};

@@ -59,6 +59,11 @@ SHAPES = [
     (20, 77, 12, [21, 96, 96, 1], "ReLU", "hjb"),                    # two layers, odd chunk counts, |Z|^2 driver
     (6, 50, 9, [7, 128, 1], "Sine", "bsb"),                          # one hidden layer: no B sweep
     (100, 64, 20, [101, 192, 256, 64, 224, 160, 1], "Sine", "hjb"),  # five layers
+    # widths that are multiples of 64 all the way (the TMEM-operand kernel's domain) with 1, 2 and 5 hidden layers, 2 / 4 / 6 / 8
+    # chunks per link (with and without parked accumulator chunks), several tiles per CTA
+    (100, 50, 20, [101, 256, 1], "Sine", "bsb"),
+    (60, 900, 30, [61, 128, 64, 1], "Tanh", "bsb"),
+    (100, 500, 40, [101, 64, 128, 256, 192, 64, 1], "Sine", "hjb"),   # (smooth activation: a ReLU unit at its kink may flip between dispatches)
 ]
 
 

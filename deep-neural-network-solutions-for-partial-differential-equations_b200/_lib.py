@@ -49,20 +49,35 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into libfbsnn_b200.so next to this file (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into libfbsnn_b200.so next to this file (nvcc cross-compiles without a GPU).
+    Safe when several processes (the ranks of a torchrun job) find the library stale at the same time: one of them builds
+    under an exclusive file lock, into a temporary file that is renamed into place; the others wait and find it fresh."""
+    import fcntl
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libfbsnn_b200.so (and there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    with open(HASH_PATH, "w") as fh:
-        fh.write(_src_hash())
+    with open(LIB_PATH + ".lock", "w") as lock_fh:
+        fcntl.flock(lock_fh, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():       # another process built it while this one waited for the lock
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + SOURCES
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, LIB_PATH)
+            with open(HASH_PATH + ".tmp", "w") as fh:
+                fh.write(_src_hash())
+            os.replace(HASH_PATH + ".tmp", HASH_PATH)
+        finally:
+            fcntl.flock(lock_fh, fcntl.LOCK_UN)
     return LIB_PATH
 
 

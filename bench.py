@@ -79,6 +79,9 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 3.0:   # nvidia-smi needs a few hundred ms for its first line
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 

@@ -9,6 +9,7 @@
 // epilogue stores a partial tile; a deterministic second pass sums the partials (no atomics anywhere).
 // All output widths N and leading dimensions of epilogue arrays are multiples of 4 (float4 epilogue I/O).
 #pragma once
+#include <type_traits>
 #include <cstring>
 
 #include "common.cuh"
@@ -453,6 +454,15 @@ inline cudaError_t launch_gemm(const GemmArgs& g, const Epi& epi, int nsplit, in
     gemm_simt_kernel<128, 128, 16, 8, 8, A_KC, B_KC, Epi><<<grid, 256, 0, st>>>(g, epi);
   } else {
     dim3 grid((g.M + 63) / 64, (g.N + 63) / 64, nsplit);
+    if constexpr (std::is_same<Epi, EpiStore>::value) {
+      // the NAIS-Net projection products (W^T W, W S: 256 x 256 x 256) are 16 CTAs of 64 x 64: a quarter of the chip for
+      // 21 us, six times per small-batch step -- 32 x 32 tiles (64 threads, same k order, so the same bits) use 64 CTAs
+      if ((long long)grid.x * grid.y * grid.z * 4 <= num_sms) {
+        dim3 grid32((g.M + 31) / 32, (g.N + 31) / 32, nsplit);
+        gemm_simt_kernel<32, 32, 16, 4, 4, A_KC, B_KC, Epi><<<grid32, 64, 0, st>>>(g, epi);
+        return cudaGetLastError();
+      }
+    }
     gemm_simt_kernel<64, 64, 16, 4, 4, A_KC, B_KC, Epi><<<grid, 256, 0, st>>>(g, epi);
   }
   return cudaGetLastError();

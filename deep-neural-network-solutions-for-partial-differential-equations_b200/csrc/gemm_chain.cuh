@@ -1476,6 +1476,7 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (lane == 0) {
       uint32_t t = 0, ph = 0;
+      int pending = -1;   // stage whose stores are committed but not yet known to have been read
       const uint64_t pol = l2_evict_first_policy();
       CPROF_BEGIN(true)
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -1495,15 +1496,36 @@ chaint_kernel(const __grid_constant__ Maps tm, const Args a) {
               if (L.out0) tma_store_2d(&tm.out0[i], st, 32 * j, m0);
               if (L.out2) tma_store_2d(&tm.out2[i], st + CHUNK_BYTES, 32 * j, m0);
             }
-            if (do_store) {
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (a.hints & 8) {
+              // two store groups in flight: the stage of the PREVIOUS chunk is released once its stores have read it, while
+              // this chunk's stores are already queued behind them (a store takes ~1 200 cycles from issue to "read", about as
+              // long as the MMAs of a chunk: one group at a time makes the store warp the pace-maker)
+              if (do_store) {
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (pending >= 0) tc::mbar_arrive(&io_free[pending]);
+                pending = (int)t;
+              } else {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (pending >= 0) tc::mbar_arrive(&io_free[pending]);
+                pending = -1;
+                tc::mbar_arrive(&io_free[t]);
+              }
+            } else {
+              if (do_store) {
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              tc::mbar_arrive(&io_free[t]);
             }
-            tc::mbar_arrive(&io_free[t]);
             CPROF_LAP(13)
             if (++t == IOS) t = 0, ph ^= 1;
           }
         }
+      }
+      if (pending >= 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        tc::mbar_arrive(&io_free[pending]);
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
     }

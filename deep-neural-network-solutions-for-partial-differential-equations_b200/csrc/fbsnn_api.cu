@@ -882,12 +882,19 @@ static int run_loss(const FbsnnSpec* s, const Plan& p, float* ws, bool with_grad
 // reduction for one batched launch, else it is launched right away
 static int wgrad(const FbsnnSpec* s, const Plan& p, float* ws, const float* P0, const float* Q0, const float* P1,
                  const float* Q1, int out, int in_pad, int in_valid, int ldq, float* dst, int ld_dst, cudaStream_t st,
-                 RedJobs* defer = nullptr, size_t part_off = 0) {
+                 RedJobs* defer = nullptr, size_t part_off = 0, tc2g::BatchG* batch = nullptr) {
   GemmArgs g{};
   g.M = out, g.N = in_pad, g.Nb = in_pad, g.kchunk = p.wg_chunk, g.nseg = 2;
   g.seg[0] = GemmSeg{P0, Q0, out, ldq, (int)p.rows};
   g.seg[1] = GemmSeg{P1, Q1, out, ldq, (int)p.rows};
   float* part = ws + p.part_wg + part_off;
+  // small batches: the contractions of all layers go into ONE launch of the TMEM-A pair kernel (flushed by the caller)
+  if (batch && defer && s->precision == FBSNN_PREC_TF32X3 && tc_eligible<false, false>(g, p.wg_split) &&
+      uses_pair<false, false>(s, g, p.wg_split) && gtmem_enabled() && tc2g_eligible(g, p.wg_split) &&
+      tc2g_batch_add(*batch, g, EpiPartial{part, out, in_pad}, p.wg_split)) {
+    defer->job[defer->njobs++] = RedJob{part, dst, out, in_pad, in_valid, ld_dst};
+    return 0;
+  }
   int rc = dense<false, false>(s, g, EpiPartial{part, out, in_pad}, p.wg_split, st, "G");
   if (rc) return rc;
   if (defer) {
@@ -964,6 +971,38 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
   RedJobs* defer = (!p.nais || p.wg_slots > 1) ? &red : nullptr;
   const size_t wg_stride = p.wg_stride;
   int slot = 0;
+  // below ~2 row tiles per SM a contraction is a few k-blocks per CTA: all of them in one launch (gemm_tc2g_batched_kernel)
+  tc2g::BatchG bt;
+  bt.njobs = 0, bt.nsplit = 0;
+  static int gbatch = -1;
+  if (gbatch < 0) {
+    const char* e = getenv("FBSNN_GBATCH");
+    gbatch = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 0;
+  }
+  tc2g::BatchG* batch = (gbatch && defer && p.rows <= (long long)num_sms() * 256) ? &bt : nullptr;
+  auto flush_batch = [&]() -> int {
+    if (!batch || bt.njobs == 0) return 0;
+    int tslot = -1;
+    if (g_timing && g_ntimed < kMaxTimed) {
+      tslot = g_ntimed++;
+      if (!g_ev0[tslot]) cudaEventCreate(&g_ev0[tslot]), cudaEventCreate(&g_ev1[tslot]);
+      double fl = 0, by = 0;
+      for (int j = 0; j < bt.njobs; ++j) {
+        double k = 0;
+        for (int i = 0; i < bt.g[j].nseg; ++i) k += bt.g[j].seg[i].K;
+        fl += 2.0 * (double)bt.g[j].M * (double)bt.g[j].N * k;
+        by += 4.0 * (k * ((double)bt.g[j].M + (double)bt.g[j].N) + (double)bt.g[j].M * (double)bt.g[j].N * bt.nsplit);
+      }
+      g_flops[tslot] = fl, g_bytes[tslot] = by, g_timed_tc[tslot] = true, g_timed_what[tslot] = "G";
+      cudaEventRecord(g_ev0[tslot], st);
+    }
+    ++g_launches;
+    const cudaError_t e = launch_gemm_tc2g_batched(bt, num_sms(), st);
+    if (tslot >= 0) cudaEventRecord(g_ev1[tslot], st);
+    bt.njobs = 0;
+    if (e != cudaSuccess) return fail(FBSNN_E_CUDA, "tcgen05 batched weight gradients: %s", cudaGetErrorString(e));
+    return 0;
+  };
   auto nais_wbar = [&](int l) -> int {   // gradient through the stability projection: Wbar_l = W_l (Rbar + Rbar^T)
     const int H = p.H[l];
     nais_project_bwd_kernel<<<(H * H + 1023) / 1024, 1024, 0, st>>>(ws + p.Bbar[l], ws + p.Rm[l], H, ws + p.nstate[l], ws + p.Sm[l]);
@@ -977,20 +1016,24 @@ static int sweeps_backward(const FbsnnSpec* s, const Plan& p, const Net& n, floa
     int rc;
     if (l == 1) {
       rc = wgrad(s, p, ws, ws + p.szz[1], ws + p.xin, ws + p.delta[1], ws + p.V, p.H[1], p.ldx, p.d_in, p.ldx,
-                 grads + s->off_W[1], p.d_in, st, defer, defer ? (size_t)(slot++) * wg_stride : 0);
+                 grads + s->off_W[1], p.d_in, st, defer, defer ? (size_t)(slot++) * wg_stride : 0, batch);
       if (rc) return rc;
       continue;
     }
     float* dst = p.nais ? ws + p.Bbar[l] : grads + s->off_W[l];
     rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.h[l - 1], ws + p.delta[l], ws + p.hd[l - 1], p.H[l], p.H[l - 1],
-               p.H[l - 1], p.H[l - 1], dst, p.H[l - 1], st, defer, defer ? (size_t)(slot++) * wg_stride : 0);
+               p.H[l - 1], p.H[l - 1], dst, p.H[l - 1], st, defer, defer ? (size_t)(slot++) * wg_stride : 0, batch);
     if (rc) return rc;
     if (p.nais) {
       rc = wgrad(s, p, ws, ws + p.szz[l], ws + p.xin, ws + p.delta[l], ws + p.V, p.H[l], p.ldx, p.d_in, p.ldx,
-                 grads + s->off_Win[l], p.d_in, st, defer, defer ? (size_t)(slot++) * wg_stride : 0);
+                 grads + s->off_Win[l], p.d_in, st, defer, defer ? (size_t)(slot++) * wg_stride : 0, batch);
       if (rc) return rc;
       if (!defer && (rc = nais_wbar(l))) return rc;
     }
+  }
+  {
+    int rc = flush_batch();
+    if (rc) return rc;
   }
   if (defer && red.njobs > 0) {
     int maxn = 0;

@@ -53,9 +53,11 @@ __device__ __forceinline__ void umma_tf32_pair_ts(uint32_t tmem_d, uint32_t tmem
       : "memory");
 }
 
+// body of one CTA of cluster `cid` of `ncl` clusters working on the split-K chunks of ONE contraction (tma / tmb = its
+// tensor maps, in kernel-parameter space)
 template <class Epi>
-__global__ void __launch_bounds__(NUM_THREADS_G, 1)
-gemm_tc2g_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi, const int nsplit) {
+__device__ __forceinline__ void tc2g_body(const CUtensorMap* tma, const CUtensorMap* tmb, const GemmArgs& g, const Epi& epi,
+                                          const int nsplit, const int cid, const int ncl) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* epi_tiles = (float*)(smem + STAGES_G * STAGE_G_BYTES);
@@ -71,13 +73,12 @@ gemm_tc2g_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi e
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int N = g.N, NH = N >> 1;
-  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int num_work = nsplit;         // one 256 x N output per split-K chunk
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nseg; ++s) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.a[s]) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b[s]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tma[s]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmb[s]) : "memory");
     }
     for (int i = 0; i < STAGES_G; ++i)
       mbar_init(&full[i], 1), mbar_init(&empty[i], 1), mbar_init(&sdone[i], 2);   // one arrival per CTA
@@ -111,8 +112,8 @@ gemm_tc2g_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi e
             mbar_expect_tx(&full[stage], bytes);
             uint8_t* a = smem + stage * STAGE_G_BYTES;
             uint8_t* b = a + A_ROWMAJOR_BYTES;
-            tma_load_2d(a, &tm.a[s], &full[stage], m0, k0);                         // P[k0.., m0 .. m0+128), row-major
-            for (int c = 0; c < NH / 32; ++c) tma_load_2d(b + c * 4096, &tm.b[s], &full[stage], n0 + 32 * c, k0);
+            tma_load_2d(a, &tma[s], &full[stage], m0, k0);                          // P[k0.., m0 .. m0+128), row-major
+            for (int c = 0; c < NH / 32; ++c) tma_load_2d(b + c * 4096, &tmb[s], &full[stage], n0 + 32 * c, k0);
             if (++stage == STAGES_G) stage = 0, phase ^= 1;
           }
         }
@@ -249,6 +250,27 @@ gemm_tc2g_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi e
   }
 }
 
+template <class Epi>
+__global__ void __launch_bounds__(NUM_THREADS_G, 1)
+gemm_tc2g_kernel(const __grid_constant__ TmSet tm, const GemmArgs g, const Epi epi, const int nsplit) {
+  tc2g_body(tm.a, tm.b, g, epi, nsplit, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1));
+}
+
+// Several contractions in ONE launch (blockIdx.y = job): the weight gradients of all layers of a small-batch step, each of
+// which alone would be a launch of a few k-blocks per CTA (M = 100: 4 launches of 14-17 us, mostly prologue and drain).
+constexpr int kMaxJobsG = 8;
+struct BatchG {
+  CUtensorMap a[kMaxJobsG][2], b[kMaxJobsG][2];   // two segments per contraction
+  GemmArgs g[kMaxJobsG];
+  EpiPartial epi[kMaxJobsG];
+  int njobs, nsplit;
+};
+__global__ void __launch_bounds__(NUM_THREADS_G, 1)
+gemm_tc2g_batched_kernel(const __grid_constant__ BatchG bt) {
+  const int j = blockIdx.y;
+  tc2g_body(bt.a[j], bt.b[j], bt.g[j], bt.epi[j], bt.nsplit, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1));
+}
+
 // 2-D fp32 tensor map without swizzle (the P tile is read by threads, not by the tensor core)
 inline bool make_map_plain(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld,
                            int box_inner, int box_outer) {
@@ -291,6 +313,52 @@ inline cudaError_t launch_gemm_tc2g(const GemmArgs& g, const Epi& epi, int nspli
   }
   const int ncl = std::min(nsplit, num_sms / 2);
   return tc::launch_pdl(kern, 2 * ncl, tc2g::NUM_THREADS_G, tc2g::SMEM_G_BYTES, st, 2, tm, g, epi, nsplit);
+}
+
+// adds one contraction to a batch; false if it does not fit (caller launches it on its own)
+inline bool tc2g_batch_add(tc2g::BatchG& bt, const GemmArgs& g, const EpiPartial& epi, int nsplit) {
+  if (bt.njobs >= tc2g::kMaxJobsG || g.nseg > 2 || (bt.njobs > 0 && bt.nsplit != nsplit)) return false;
+  const int j = bt.njobs;
+  for (int s = 0; s < g.nseg; ++s) {
+    const GemmSeg& sg = g.seg[s];
+    bool ok = tc2g::make_map_plain(&bt.a[j][s], sg.A, g.M, sg.K, sg.lda, 128, tc::BK);
+    ok = ok && tc::make_map(&bt.b[j][s], sg.B, g.Nb, sg.K, sg.ldb, 32, 32, true);
+    if (!ok) return false;
+  }
+  for (int s = g.nseg; s < 2; ++s) bt.a[j][s] = bt.a[j][0], bt.b[j][s] = bt.b[j][0];
+  bt.g[j] = g, bt.epi[j] = epi, bt.nsplit = nsplit;
+  ++bt.njobs;
+  return true;
+}
+inline cudaError_t launch_gemm_tc2g_batched(const tc2g::BatchG& bt, int num_sms, cudaStream_t st) {
+  auto kern = tc2g::gemm_tc2g_batched_kernel;
+  static unsigned long long attr_devs = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return cudaErrorInvalidDevice;
+  if (!((attr_devs >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2g::SMEM_G_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_devs |= 1ull << dev;
+  }
+  const int ncl = std::max(1, std::min(bt.nsplit, num_sms / 2 / bt.njobs));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * ncl, bt.njobs, 1);
+  cfg.blockDim = dim3(tc2g::NUM_THREADS_G, 1, 1);
+  cfg.dynamicSmemBytes = tc2g::SMEM_G_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeClusterDimension;
+  attr[n].val.clusterDim.x = 2, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+  ++n;
+  if (tc::pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, bt);
 }
 
 }  // namespace fbsnn

@@ -105,7 +105,8 @@ def test_chained_sweeps_match_per_layer(shape, precision, chain_forced):
 
 
 def test_chained_dispatch_is_what_runs(chain_forced):
-    """With the option forced the 4x256 network must take 4 chained launches + 4 weight-gradient contractions."""
+    """With the option forced the 4x256 network must take 4 chained launches + the weight-gradient contractions (one batched
+    launch at this batch size)."""
     import dnnpde_b200 as pde
     lib = chain_forced
     torch.manual_seed(0)
@@ -127,7 +128,8 @@ def test_chained_dispatch_is_what_runs(chain_forced):
         tags.append(tag.decode())
         i += 1
     lib.fbsnn_dense_timing(0)
-    assert tags == ["F*", "A*", "T*", "B*", "G", "G", "G", "G"], tags
+    # small batch: the four weight-gradient contractions share one launch (gemm_tc2g_batched_kernel)
+    assert tags in (["F*", "A*", "T*", "B*", "G"], ["F*", "A*", "T*", "B*", "G", "G", "G", "G"]), tags
 
 
 FC_CASES = [n for n in gu.solver_cases() if "_fc_" in n]

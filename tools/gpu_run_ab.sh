@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU call AB: batched weight-gradient launch at small batches: parity, M = 100 launch list, small-M points, NAIS workloads
-mkdir -p gpurun_out
+mkdir -p gpurun_out; export FBSNN_GBATCH=1
 O=gpurun_out
 ( timeout 1200 python -m pytest tests/test_parity_gpu.py tests/test_properties_gpu.py tests/test_round2_gpu.py tests/test_gemm_gpu.py -m gpu -q -x ) > $O/ab_pytest.log 2>&1; echo "pytest rc=$?"
 tail -3 $O/ab_pytest.log

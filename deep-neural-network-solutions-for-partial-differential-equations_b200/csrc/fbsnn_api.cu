@@ -130,6 +130,16 @@ static void make_plan(const FbsnnSpec* s, long long rows, bool with_grad, Plan& 
   // wants (M tiles) x splits ~ one work item per SM, and fewer partial tiles to reduce afterwards
   int split = (int)std::min<long long>(std::max<long long>((rows + 511) / 512, 1), 256);
   if (s->precision != FBSNN_PREC_FP32) split = (int)std::min<long long>(std::max<long long>((rows + 63) / 64, 1), 74);
+  // small 3xTF32 batches run the contractions of all layers in one batched launch (sweeps_backward): one work item per CTA
+  // pair, i.e. SMs / 2 / contractions splits each -- fewer accumulator drains and a third of the partials to reduce
+  // (only when every contraction is one the batched kernel takes: 256 outputs, input widths multiples of 64 -- the others
+  // run as launches of their own and want the parallelism)
+  bool batchable = s->precision == FBSNN_PREC_TF32X3 && rows <= (long long)num_sms() * 256 && p.ldx % 64 == 0;
+  for (int l = 1; l <= p.L; ++l) batchable = batchable && p.H[l] == 256;
+  if (batchable) {
+    const int jobs = p.nais ? 2 * p.L - 1 : p.L;
+    split = std::min(split, std::max(1, num_sms() / 2 / std::max(jobs, 1)));
+  }
   p.wg_chunk = round_up((rows + split - 1) / split, 32);   // multiple of the tcgen05 kernel's BLOCK_K
   p.wg_split = (int)((rows + p.wg_chunk - 1) / p.wg_chunk);
   p.gsq_blocks = 256;

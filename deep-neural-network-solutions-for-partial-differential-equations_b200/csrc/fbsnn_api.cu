@@ -773,7 +773,7 @@ static int chain_backward(const FbsnnSpec* s, const Plan& p, const Net& n, float
     int rc = chain_launch<chain::SWEEP_B>(s, p, m, a, "B*", st);
     if (rc) return rc;
   }
-  chain::chain_colsum_finish_kernel<<<dim3(1, fin.njobs), 256, 0, st>>>(colacc, fin);
+  chain::chain_colsum_finish_kernel<<<dim3(8, fin.njobs), 256, 0, st>>>(colacc, fin);   // 8 lanes per column, widths <= 256
   LAUNCH_CHECK("chain_colsum_finish");
   return 0;
 }

@@ -1589,16 +1589,22 @@ struct ColFinJobs {
   int njobs, nblk;
 };
 __global__ void chain_colsum_finish_kernel(const float* __restrict__ colacc, const ColFinJobs js) {
+  // eight lanes per column: lane k adds the CTAs b = k, k + 8, ... (row quarters in order), then the eight partial sums are
+  // combined in a fixed tree -- deterministic, and 20 instead of 160 dependent-latency loads per thread at M = 100
   const ColFinJob& j = js.job[blockIdx.y];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= j.width) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = t >> 3, k = t & 7;
   double acc = 0.0;
-  for (int b = 0; b < js.nblk; ++b) {
-    const float* p = colacc + ((size_t)(b * kMaxLinks + j.slot) * 2 + j.which) * 1024 + c;
+  if (c < j.width) {
+    for (int b = k; b < js.nblk; b += 8) {
+      const float* p = colacc + ((size_t)(b * kMaxLinks + j.slot) * 2 + j.which) * 1024 + c;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc += (double)p[q * 256];
+      for (int q = 0; q < 4; ++q) acc += (double)p[q * 256];
+    }
   }
-  j.out[c] = (float)acc;
+#pragma unroll
+  for (int off = 4; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off, 8);
+  if (c < j.width && k == 0) j.out[c] = (float)acc;
 }
 
 inline int chain_grid(int ntiles, int num_sms) { return ntiles < num_sms ? ntiles : num_sms; }

@@ -163,8 +163,13 @@ def workload_config(args):
 def ref_subprocess(argv, timeout=900):
     """Run baseline/ref_bench.py in its own process (CUDA hidden there) and parse its JSON line."""
     try:
+        # all the host threads the reference can use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the
+        # reference on ONE core (7.0 instead of 0.9 s per 1000-path iteration)
+        env = dict(os.environ)
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            env[k] = str(os.cpu_count() or 1)
         r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_bench.py")] + argv, capture_output=True,
-                           text=True, timeout=timeout)
+                           text=True, timeout=timeout, env=env)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)
@@ -205,6 +210,7 @@ def cpu_baseline_block(args, steps, warmup, suite):
         sec, kind = port_train_rate(min(sample, 256), steps, warmup), "port"
         sample = min(sample, 256)
         how = "oracle port of the DeepBSDE.py train loop (baseline/_ref not installed: " + str(res.get("error", ""))[:80] + ")"
+    cores = res.get("torch_threads") or cores            # the threads the reference actually ran on
     out = {"value": 1.0 / sec, "unit": "iters/s", "cores": cores, "kind": kind,
            "sample": f"{sample}-path minibatches of the {args.paths}-path workload, {steps} measured iterations "
                      f"({sec:.3f} s each); {how}",
